@@ -1,0 +1,161 @@
+"""ctypes loader for libh263cu.so (the C ABI declared in include/h263cu.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `h263_rs_b200.build`.
+There is no CPU fallback: a missing library raises, and device entry points return
+H263CU_ERR_NO_DEVICE / H263CU_ERR_CUDA without a GPU.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("H263CU_LIB", os.path.join(HERE, "libh263cu.so"))
+
+OK = 0
+ERR_UNHANDLED_IO_ERROR = -16
+ERR_BAD_ARGUMENT = -100
+ERR_CUDA = -101
+ERR_NO_DEVICE = -102
+ERR_CAPACITY = -103
+ERR_REFERENCE_WOULD_ABORT = -104
+ERR_NO_PICTURE = -105
+
+OPT_SORENSON = 1
+OUT_RGBA = 1
+OUT_DEBLOCK = 2
+
+PIC_I, PIC_P, PIC_DISPOSABLE_P, PIC_OTHER = 0, 1, 2, 3
+MB_INTER, MB_WIDE, MB_FOURMV, MB_CODED = 1, 2, 4, 8
+
+
+class Pic(C.Structure):
+    _fields_ = [
+        ("stream", C.c_uint32), ("width", C.c_uint16), ("height", C.c_uint16), ("mb_w", C.c_uint8),
+        ("mb_h", C.c_uint8), ("pic_type", C.c_uint8), ("pquant", C.c_uint8), ("flags", C.c_uint8),
+        ("version", C.c_uint8), ("temporal_reference", C.c_uint16), ("first_mb", C.c_uint32), ("n_mbs", C.c_uint32),
+        ("first_event", C.c_uint32), ("n_event_units", C.c_uint32),
+    ]
+
+
+class MbUnion(C.Union):
+    _fields_ = [("mv", (C.c_int8 * 2) * 4), ("intradc", C.c_uint8 * 6)]
+
+
+class Mb(C.Structure):
+    _fields_ = [
+        ("ev_off", C.c_uint32), ("pic", C.c_uint16), ("mbx", C.c_uint8), ("mby", C.c_uint8), ("flags", C.c_uint8),
+        ("quant", C.c_uint8), ("nev", C.c_uint8 * 6), ("u", MbUnion),
+    ]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("n_pictures", C.c_uint32), ("seed", C.c_uint64),
+        ("flavour", C.c_uint32), ("version", C.c_uint32), ("intra_period", C.c_uint32), ("deblock_flag", C.c_uint32),
+        ("qp_min", C.c_uint32), ("qp_max", C.c_uint32), ("pct_uncoded", C.c_uint32), ("pct_intra", C.c_uint32),
+        ("pct_fourmv", C.c_uint32), ("pct_dquant", C.c_uint32), ("pct_cbp_inter", C.c_uint32),
+        ("pct_cbp_intra", C.c_uint32), ("mean_events_x10", C.c_uint32), ("pct_escape", C.c_uint32),
+        ("permille_overflow", C.c_uint32), ("mv_mode", C.c_uint32), ("truncate_permille", C.c_uint32),
+        ("reserved", C.c_uint32 * 4),
+    ]
+
+
+assert C.sizeof(Pic) == 32 and C.sizeof(Mb) == 24
+
+# Every symbol include/h263cu.h declares; tests check that the library exports all of them.
+SYMBOLS = [
+    "h263cu_is_eof_error", "h263cu_is_macroblock_error", "h263cu_is_gob_error", "h263cu_strerror",
+    "h263cu_version", "h263cu_parser_create", "h263cu_parser_destroy", "h263cu_parser_reset",
+    "h263cu_peek_picture", "h263cu_parse_picture", "h263cu_parse_step", "h263cu_device_count",
+    "h263cu_create", "h263cu_destroy", "h263cu_device_of", "h263cu_alloc_pinned", "h263cu_free_pinned",
+    "h263cu_step_upload", "h263cu_step_free", "h263cu_step_run", "h263cu_submit_step",
+    "h263cu_submit_step_readback", "h263cu_sync", "h263cu_stream_info", "h263cu_read_yuv", "h263cu_read_rgba",
+    "h263cu_checksums", "h263cu_timer_start", "h263cu_timer_stop", "h263cu_launch_count",
+    "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength", "h263cu_synth_default_params",
+    "h263cu_synth_stream",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libh263cu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libh263cu.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "this package has no CPU fallback" % LIB_PATH
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.h263cu_strerror.restype = C.c_char_p
+    L.h263cu_strerror.argtypes = [i32]
+    L.h263cu_parser_create.restype = vp
+    L.h263cu_parser_create.argtypes = [u32]
+    L.h263cu_parser_destroy.argtypes = [vp]
+    L.h263cu_parser_destroy.restype = None
+    L.h263cu_parser_reset.argtypes = [vp]
+    L.h263cu_parser_reset.restype = None
+    L.h263cu_peek_picture.argtypes = [u32, C.c_char_p, C.c_size_t, C.POINTER(Pic)]
+    L.h263cu_parse_picture.argtypes = [vp, C.c_char_p, C.c_size_t, u32, C.c_uint16, u32, u32, C.POINTER(Pic), vp, u32,
+                                       vp, u32]
+    L.h263cu_parse_step.argtypes = [vp, vp, vp, vp, u32, i32, vp, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32),
+                                    C.POINTER(u32), vp, vp]
+    if hasattr(L, "h263cu_create"):
+        L.h263cu_create.restype = vp
+        L.h263cu_create.argtypes = [i32, u32, u32, u32, u32, C.POINTER(i32)]
+        L.h263cu_destroy.argtypes = [vp]
+        L.h263cu_destroy.restype = None
+        L.h263cu_device_of.argtypes = [vp]
+        L.h263cu_alloc_pinned.restype = vp
+        L.h263cu_alloc_pinned.argtypes = [C.c_size_t]
+        L.h263cu_free_pinned.argtypes = [vp]
+        L.h263cu_free_pinned.restype = None
+        L.h263cu_step_upload.restype = vp
+        L.h263cu_step_upload.argtypes = [vp, vp, u32, vp, u32, vp, u32, C.POINTER(i32)]
+        L.h263cu_step_free.argtypes = [vp, vp]
+        L.h263cu_step_free.restype = None
+        L.h263cu_step_run.argtypes = [vp, vp, u32]
+        L.h263cu_submit_step.argtypes = [vp, vp, u32, vp, u32, vp, u32, u32]
+        L.h263cu_submit_step_readback.argtypes = [vp, vp, u32, vp, u32, vp, u32, u32, vp, vp]
+        L.h263cu_sync.argtypes = [vp]
+        L.h263cu_stream_info.argtypes = [vp, u32] + [C.POINTER(u32)] * 5
+        L.h263cu_read_yuv.argtypes = [vp, u32, vp, vp, vp]
+        L.h263cu_read_rgba.argtypes = [vp, u32, vp]
+        L.h263cu_checksums.argtypes = [vp, vp, u32, vp]
+        L.h263cu_timer_start.argtypes = [vp]
+        L.h263cu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+        L.h263cu_launch_count.restype = u64
+        L.h263cu_launch_count.argtypes = [vp]
+        L.h263cu_yuv420_to_rgba.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, vp]
+        L.h263cu_deblock.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_uint8, vp]
+    L.h263cu_synth_default_params.argtypes = [C.POINTER(SynthParams), u32, u32, u32, u64]
+    L.h263cu_synth_default_params.restype = None
+    L.h263cu_synth_stream.restype = C.c_int64
+    L.h263cu_synth_stream.argtypes = [C.POINTER(SynthParams), vp, C.c_size_t, vp, vp]
+    _lib = L
+    return L
+
+
+class H263Error(Exception):
+    """Mirror of h263::Error (error.rs:6-57) plus the library's own failures."""
+
+    def __init__(self, code):
+        self.code = code
+        super().__init__("%s (%d)" % (lib().h263cu_strerror(code).decode(), code))
+
+    def is_eof_error(self):
+        return bool(lib().h263cu_is_eof_error(self.code))
+
+    def is_macroblock_error(self):
+        return bool(lib().h263cu_is_macroblock_error(self.code))
+
+    def is_gob_error(self):
+        return bool(lib().h263cu_is_gob_error(self.code))
+
+
+def check(code):
+    if code < 0:
+        raise H263Error(code)
+    return code

@@ -1,0 +1,244 @@
+"""Host-side mirror of the reference's public API, backed by libh263cu.so.
+
+Names, argument meaning and error behaviour follow the reference so that the parity
+tests read like the reference's own tests:
+
+    h263::H263State::{new, decode_next_picture, get_last_picture, is_sorenson}   state.rs:40-141
+    h263::DecodedPicture::{as_yuv, as_luma, as_chroma_b, as_chroma_r, ...}         picture.rs:60-142
+    yuv::bt601::yuv420_to_rgba(y, chroma_b, chroma_r, y_width) -> Vec<u8>          bt601.rs:105
+    deblock::deblock::deblock(data, width, strength) -> Vec<u8>, QUANT_TO_STRENGTH deblock.rs:5-8,305
+
+plus `BatchDecoder`, the batched form the GPU path is built for (one picture for each of
+many independent streams per step).  All compute runs on the GPU through the C ABI; there
+is no CPU fallback (errors surface as H263Error).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, frontend
+from ._lib import H263Error, check
+
+SORENSON_SPARK_BITSTREAM = _lib.OPT_SORENSON
+USE_SCALABILITY_MODE = 2
+
+
+def _quant_to_strength():
+    arr = (C.c_uint8 * 32).in_dll(_lib.lib(), "h263cu_quant_to_strength")
+    return [int(v) for v in arr]
+
+
+class _LazyTable:
+    def __init__(self):
+        self._v = None
+
+    def _get(self):
+        if self._v is None:
+            self._v = _quant_to_strength()
+        return self._v
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __len__(self):
+        return 32
+
+    def __iter__(self):
+        return iter(self._get())
+
+
+QUANT_TO_STRENGTH = _LazyTable()
+
+
+def yuv420_to_rgba(y, chroma_b, chroma_r, y_width):
+    """yuv::bt601::yuv420_to_rgba: planar YUV 4:2:0 -> interleaved RGBA8888 (GPU)."""
+    y = np.ascontiguousarray(y, np.uint8).reshape(-1)
+    cb = np.ascontiguousarray(chroma_b, np.uint8).reshape(-1)
+    cr = np.ascontiguousarray(chroma_r, np.uint8).reshape(-1)
+    out = np.empty(y.size * 4, np.uint8)
+    if y.size == 0:
+        return out
+    check(_lib.lib().h263cu_yuv420_to_rgba(y.ctypes.data, cb.ctypes.data, cr.ctypes.data, y.size, y_width,
+                                           out.ctypes.data))
+    return out
+
+
+def deblock(data, width, strength):
+    """deblock::deblock::deblock: Annex-J-style post filter on one plane (GPU)."""
+    data = np.ascontiguousarray(data, np.uint8).reshape(-1)
+    out = np.empty(data.size, np.uint8)
+    if data.size == 0:
+        return out
+    check(_lib.lib().h263cu_deblock(data.ctypes.data, data.size, width, strength, out.ctypes.data))
+    return out
+
+
+class DecodedPicture:
+    """Mirror of h263::DecodedPicture: header fields + tight row-major u8 planes."""
+
+    def __init__(self, width, height, picture_type, quantizer, temporal_reference, y, cb, cr):
+        self.width, self.height = width, height
+        self.picture_type = picture_type
+        self.quantizer = quantizer
+        self.temporal_reference = temporal_reference
+        self._y, self._cb, self._cr = y, cb, cr
+
+    def as_yuv(self):
+        return self._y, self._cb, self._cr
+
+    def as_luma(self):
+        return self._y
+
+    def as_chroma_b(self):
+        return self._cb
+
+    def as_chroma_r(self):
+        return self._cr
+
+    def luma_samples_per_row(self):
+        return self.width
+
+    def chroma_samples_per_row(self):
+        return (self.width + 1) // 2
+
+
+class Context:
+    """Thin RAII wrapper of h263cu_ctx."""
+
+    def __init__(self, device, max_streams, max_width, max_height):
+        self.L = _lib.lib()
+        err = C.c_int(0)
+        self.h = self.L.h263cu_create(device, max_streams, max_width, max_height, 0, C.byref(err))
+        if not self.h:
+            raise H263Error(err.value)
+        self.max_streams, self.max_width, self.max_height = max_streams, max_width, max_height
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.h263cu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def submit_step(self, pics, mbs, events, out_flags):
+        check(self.L.h263cu_submit_step(self.h, pics.ctypes.data, len(pics), mbs.ctypes.data, len(mbs),
+                                        events.ctypes.data if len(events) else None, len(events), out_flags))
+
+    def step_upload(self, pics, mbs, events):
+        err = C.c_int(0)
+        s = self.L.h263cu_step_upload(self.h, pics.ctypes.data, len(pics), mbs.ctypes.data, len(mbs),
+                                      events.ctypes.data if len(events) else None, len(events), C.byref(err))
+        if not s:
+            raise H263Error(err.value)
+        return s
+
+    def step_run(self, step, out_flags):
+        check(self.L.h263cu_step_run(self.h, step, out_flags))
+
+    def step_free(self, step):
+        self.L.h263cu_step_free(self.h, step)
+
+    def sync(self):
+        check(self.L.h263cu_sync(self.h))
+
+    def stream_info(self, stream):
+        v = [C.c_uint32() for _ in range(5)]
+        check(self.L.h263cu_stream_info(self.h, stream, *[C.byref(x) for x in v]))
+        return dict(zip(("width", "height", "pic_type", "pquant", "tr"), [x.value for x in v]))
+
+    def read_yuv(self, stream):
+        i = self.stream_info(stream)
+        w, h = i["width"], i["height"]
+        cw, ch = (w + 1) // 2, (h + 1) // 2
+        y = np.empty(w * h, np.uint8)
+        cb = np.empty(cw * ch, np.uint8)
+        cr = np.empty(cw * ch, np.uint8)
+        check(self.L.h263cu_read_yuv(self.h, stream, y.ctypes.data, cb.ctypes.data, cr.ctypes.data))
+        return y, cb, cr
+
+    def read_rgba(self, stream):
+        i = self.stream_info(stream)
+        out = np.empty(i["width"] * i["height"] * 4, np.uint8)
+        check(self.L.h263cu_read_rgba(self.h, stream, out.ctypes.data))
+        return out
+
+    def checksums(self, streams):
+        s = np.ascontiguousarray(streams, np.uint32)
+        out = np.zeros((len(s), 4), np.uint64)
+        check(self.L.h263cu_checksums(self.h, s.ctypes.data, len(s), out.ctypes.data))
+        return out
+
+    def timer_start(self):
+        check(self.L.h263cu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.L.h263cu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.L.h263cu_launch_count(self.h))
+
+
+class H263State:
+    """Mirror of h263::H263State for ONE stream: host parse + GPU reconstruction.
+
+    `decode_next_picture(packet)` takes the bytes of one picture (the reference reads them
+    through `H263Reader::from_source(&packet[..])`; Sorenson pictures end at EOF, so one
+    reader per packet is the only usable form)."""
+
+    def __init__(self, decoder_options=SORENSON_SPARK_BITSTREAM, device=0, deblock=False):
+        self.decoder_options = decoder_options
+        self.device = device
+        self.parser = frontend.Parser(decoder_options)
+        self.ctx = None
+        self.out_flags = _lib.OUT_RGBA | (_lib.OUT_DEBLOCK if deblock else 0)
+        self._has_picture = False
+
+    def is_sorenson(self):
+        return bool(self.decoder_options & SORENSON_SPARK_BITSTREAM)
+
+    def decode_next_picture(self, packet):
+        pic, mbs, events = self.parser.parse_picture(bytes(packet))
+        w, h = int(pic["width"][0]), int(pic["height"][0])
+        if self.ctx is None or w > self.ctx.max_width or h > self.ctx.max_height:
+            self.ctx = Context(self.device, 1, max(w, 16), max(h, 16))
+        self.ctx.submit_step(pic, mbs, events, self.out_flags)
+        self.ctx.sync()
+        self._has_picture = True
+
+    def get_last_picture(self):
+        if not self._has_picture:
+            return None
+        i = self.ctx.stream_info(0)
+        y, cb, cr = self.ctx.read_yuv(0)
+        return DecodedPicture(i["width"], i["height"], i["pic_type"], i["pquant"], i["tr"], y, cb, cr)
+
+    def get_last_rgba(self):
+        """RGBA of the last picture (fused yuv420_to_rgba, or deblock + yuv420_to_rgba)."""
+        if not self._has_picture:
+            return None
+        return self.ctx.read_rgba(0)
+
+
+class BatchDecoder:
+    """n independent streams decoded in lock step: one picture per stream per step."""
+
+    def __init__(self, n_streams, max_width, max_height, decoder_options=SORENSON_SPARK_BITSTREAM, device=0,
+                 threads=0):
+        self.n = n_streams
+        self.parsers = [frontend.Parser(decoder_options) for _ in range(n_streams)]
+        self.ctx = Context(device, n_streams, max_width, max_height)
+        self.threads = threads
+
+    def parse_step(self, packets, stream_ids=None):
+        ids = np.arange(self.n, dtype=np.uint32) if stream_ids is None else np.asarray(stream_ids, np.uint32)
+        parsers = [self.parsers[int(s)] for s in ids]
+        return frontend.parse_step(parsers, packets, ids, self.threads)
+
+    def decode_step(self, packets, out_flags=_lib.OUT_RGBA, stream_ids=None):
+        pics, mbs, events, errs, pic_of = self.parse_step(packets, stream_ids)
+        if len(pics):
+            self.ctx.submit_step(pics, mbs, events, out_flags)
+        return errs

@@ -1,0 +1,53 @@
+"""In-tree build of libh263cu.so for sm_100a (nvcc cross-compiles without a GPU).
+
+    python -m h263_rs_b200.build [--force] [--verbose]
+
+Flags that matter:
+  -gencode arch=compute_100a,code=sm_100a   B200 only, no other targets, no PTX fallback
+  -fmad=false                               the IDCT must not contract a*b+c
+  -lineinfo                                 so ncu's source page maps SASS to these files
+The CUDA runtime is linked statically (nvcc default), so the library has no load-time
+dependency on libcudart/libcuda and can be dlopen'ed on a machine without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libh263cu.so")
+SOURCES = ["kernels.cu", "context.cu", "frontend.cpp", "synth.cpp"]
+DEPS = SOURCES + ["kernels.cuh", "device_math.cuh", "bitio.hpp", "vlc_codes.inc", os.path.join("..", "..", "include", "h263cu.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def nvcc_cmd(extra=()):
+    return [
+        NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+        "-Xcompiler", "-fPIC,-O2,-pthread,-ffp-contract=off", "-shared", "-o", OUT,
+        *[os.path.join(CSRC, s) for s in SOURCES], *extra,
+    ]
+
+
+def up_to_date():
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(os.path.join(CSRC, d)) <= t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return OUT
+    cmd = nvcc_cmd(["-Xptxas", "-v"] if verbose else [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(OUT)

@@ -1,0 +1,635 @@
+// context.cu -- device context, step objects and the device half of the C ABI
+// (include/h263cu.h).  The context owns all device memory: per stream two reconstruction
+// slots (current / reference, ping-pong) for Y, Cb, Cr and a two-deep RGBA ring; side
+// info arrives through pinned cudaMemcpyAsync.  Everything here is plumbing around the
+// kernels in kernels.cu -- there is no CPU fallback: without a usable device the entry
+// points return H263CU_ERR_NO_DEVICE / H263CU_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "device_math.cuh"
+#include "kernels.cuh"
+
+using namespace h263dev;
+
+extern "C" const uint8_t h263cu_quant_to_strength[32] = H263_QUANT_TO_STRENGTH;
+
+namespace {
+
+#define CU_TRY(expr)                      \
+    do {                                  \
+        cudaError_t _e = (expr);          \
+        if (_e != cudaSuccess) return map_cuda_error(_e); \
+    } while (0)
+
+int map_cuda_error(cudaError_t e) {
+    switch (e) {
+        case cudaErrorNoDevice:
+        case cudaErrorInsufficientDriver:
+        case cudaErrorInvalidDevice: return H263CU_ERR_NO_DEVICE;
+        case cudaErrorMemoryAllocation: return H263CU_ERR_OUT_OF_MEMORY;
+        default: return H263CU_ERR_CUDA;
+    }
+}
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct StreamState {
+    bool has_pic = false;
+    uint8_t cur_slot = 0;  // slot that holds the last decoded picture
+    int8_t rgba_slot = -1; // ring slot that holds the last picture's RGBA (-1 = none)
+    uint16_t w = 0, h = 0;
+    uint8_t pic_type = 0, pquant = 0;
+    uint16_t tr = 0;
+    uint32_t stamp = 0;
+};
+
+}  // namespace
+
+struct h263cu_step {
+    std::vector<h263cu_pic> pics;
+    h263cu_mb* d_mbs = nullptr;
+    h263cu_event* d_events = nullptr;
+    uint32_t n_mbs = 0, n_units = 0;
+    size_t mb_cap = 0, ev_cap = 0;  // capacities in elements (ring reuse)
+    uint32_t max_w = 0, max_h = 0;
+};
+
+struct h263cu_ctx {
+    int device = 0;
+    uint32_t max_streams = 0, max_w = 0, max_h = 0;
+    uint32_t mbw = 0, mbh = 0;
+    uint32_t pitch_y = 0, pitch_c = 0, rgba_pitch = 0;
+    size_t y_slot = 0, c_slot = 0, rgba_slot = 0;
+    uint8_t *y_pool = nullptr, *cb_pool = nullptr, *cr_pool = nullptr, *rgba_pool = nullptr;
+    std::vector<StreamState> streams;
+    uint32_t stamp = 0;
+    uint32_t rgba_parity = 0;
+
+    cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    // PicDev staging ring (pinned host + device)
+    static constexpr int PIC_RING = 4;
+    PicDev* h_pics[PIC_RING] = {};
+    PicDev* d_pics[PIC_RING] = {};
+    cudaEvent_t pics_done[PIC_RING] = {};
+    size_t pics_cap = 0;
+    int pic_ring_pos = 0;
+    // side-info ring used by h263cu_submit_step*
+    h263cu_step ring[2];
+    cudaEvent_t ring_h2d_done[2] = {}, ring_run_done[2] = {};
+    int ring_pos = 0;
+    // RGBA ring read-back tracking
+    cudaEvent_t rgba_written[2] = {}, rgba_read[2] = {};
+    // timing
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    uint64_t launches = 0;
+    // checksum scratch
+    ChecksumJob* d_jobs = nullptr;
+    unsigned long long* d_sums = nullptr;
+    size_t jobs_cap = 0;
+
+    uint8_t* plane(int p, uint32_t stream, int slot) const {
+        const size_t idx = (size_t)stream * 2 + (size_t)slot;
+        if (p == 0) return y_pool + idx * y_slot;
+        return (p == 1 ? cb_pool : cr_pool) + idx * c_slot;
+    }
+    uint8_t* rgba(uint32_t stream, int slot) const { return rgba_pool + ((size_t)slot * max_streams + stream) * rgba_slot; }
+};
+
+namespace {
+
+int ensure_pic_ring(h263cu_ctx* c, size_t n) {
+    if (n <= c->pics_cap) return 0;
+    CU_TRY(cudaStreamSynchronize(c->s_main));
+    size_t cap = std::max<size_t>(n, 256);
+    for (int i = 0; i < h263cu_ctx::PIC_RING; i++) {
+        if (c->h_pics[i]) cudaFreeHost(c->h_pics[i]);
+        if (c->d_pics[i]) cudaFree(c->d_pics[i]);
+        c->h_pics[i] = nullptr, c->d_pics[i] = nullptr;
+        CU_TRY(cudaHostAlloc((void**)&c->h_pics[i], cap * sizeof(PicDev), cudaHostAllocDefault));
+        CU_TRY(cudaMalloc((void**)&c->d_pics[i], cap * sizeof(PicDev)));
+    }
+    c->pics_cap = cap;
+    return 0;
+}
+
+int step_reserve(h263cu_step* s, size_t n_mbs, size_t n_units) {
+    if (n_mbs > s->mb_cap) {
+        if (s->d_mbs) cudaFree(s->d_mbs);
+        s->d_mbs = nullptr;
+        size_t cap = n_mbs + n_mbs / 8 + 64;
+        CU_TRY(cudaMalloc((void**)&s->d_mbs, cap * sizeof(h263cu_mb)));
+        s->mb_cap = cap;
+    }
+    if (n_units + 8 > s->ev_cap) {
+        if (s->d_events) cudaFree(s->d_events);
+        s->d_events = nullptr;
+        size_t cap = n_units + n_units / 8 + 64;
+        CU_TRY(cudaMalloc((void**)&s->d_events, cap * sizeof(h263cu_event)));
+        s->ev_cap = cap;
+    }
+    return 0;
+}
+
+// Validates a step against the context and the per-stream state, builds the PicDev array,
+// enqueues the kernels on s_main and advances the per-stream reference bookkeeping
+// (state.rs:464-483: the picture just decoded becomes the reference of the next one).
+int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
+    const uint32_t n = (uint32_t)s->pics.size();
+    if (n == 0) return 0;
+    if (n > 65535) return H263CU_ERR_CAPACITY;
+    const bool want_rgba = (out_flags & H263CU_OUT_RGBA) != 0;
+    const bool want_deblock = want_rgba && (out_flags & H263CU_OUT_DEBLOCK) != 0;
+    c->stamp++;
+    uint32_t max_w = 0, max_h = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const h263cu_pic& p = s->pics[i];
+        if (p.stream >= c->max_streams) return H263CU_ERR_CAPACITY;
+        if (p.width == 0 || p.height == 0 || p.width > c->max_w || p.height > c->max_h) return H263CU_ERR_CAPACITY;
+        if ((uint32_t)p.mb_w * 16 < p.width || (uint32_t)p.mb_h * 16 < p.height ||
+            (uint32_t)p.mb_w > c->mbw || (uint32_t)p.mb_h > c->mbh)
+            return H263CU_ERR_BAD_ARGUMENT;
+        if ((uint64_t)p.first_mb + p.n_mbs > s->n_mbs || (uint64_t)p.first_event + p.n_event_units > s->n_units ||
+            p.n_mbs != (uint32_t)p.mb_w * p.mb_h)
+            return H263CU_ERR_BAD_ARGUMENT;
+        StreamState& st = c->streams[p.stream];
+        if (st.stamp == c->stamp) return H263CU_ERR_BAD_ARGUMENT;  // a stream appears once per step
+        st.stamp = c->stamp;
+        if (p.flags & H263CU_PICFLAG_HAS_INTER) {
+            if (!st.has_pic) return H263CU_ERR_UNCODED_IFRAME_BLOCKS;             // gather.rs:149
+            if (st.w != p.width || st.h != p.height) return H263CU_ERR_REFERENCE_WOULD_ABORT;
+        }
+        max_w = std::max<uint32_t>(max_w, p.width);
+        max_h = std::max<uint32_t>(max_h, p.height);
+    }
+    int e = ensure_pic_ring(c, n);
+    if (e) return e;
+    const int slot = c->pic_ring_pos;
+    c->pic_ring_pos = (c->pic_ring_pos + 1) % h263cu_ctx::PIC_RING;
+    CU_TRY(cudaEventSynchronize(c->pics_done[slot]));
+    const int rgba_ring = (int)(c->rgba_parity & 1u);
+    PicDev* hp = c->h_pics[slot];
+    for (uint32_t i = 0; i < n; i++) {
+        const h263cu_pic& p = s->pics[i];
+        StreamState& st = c->streams[p.stream];
+        const int ref_slot = st.cur_slot, new_slot = st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot;
+        PicDev d;
+        std::memset(&d, 0, sizeof(d));
+        for (int k = 0; k < 3; k++) {
+            d.cur[k] = c->plane(k, p.stream, new_slot);
+            d.ref[k] = st.has_pic ? c->plane(k, p.stream, ref_slot) : nullptr;
+        }
+        d.rgba = want_rgba ? c->rgba(p.stream, rgba_ring) : nullptr;
+        d.first_event = p.first_event;
+        d.rgba_pitch = c->rgba_pitch;
+        d.w = p.width, d.h = p.height;
+        d.cw = (uint16_t)((p.width + 1) / 2), d.ch = (uint16_t)((p.height + 1) / 2);
+        d.pitch_y = (uint16_t)c->pitch_y, d.pitch_c = (uint16_t)c->pitch_c;
+        d.strength = h263cu_quant_to_strength[p.pquant & 31];
+        d.flags = p.flags;
+        hp[i] = d;
+        // bookkeeping
+        st.cur_slot = (uint8_t)new_slot;
+        st.has_pic = true;
+        st.w = p.width, st.h = p.height;
+        st.pic_type = p.pic_type, st.pquant = p.pquant, st.tr = p.temporal_reference;
+        st.rgba_slot = want_rgba ? (int8_t)rgba_ring : (int8_t)-1;
+    }
+    CU_TRY(cudaMemcpyAsync(c->d_pics[slot], hp, n * sizeof(PicDev), cudaMemcpyHostToDevice, c->s_main));
+    CU_TRY(cudaEventRecord(c->pics_done[slot], c->s_main));
+    if (want_rgba) {
+        // do not overwrite an RGBA ring slot that is still being read back
+        CU_TRY(cudaStreamWaitEvent(c->s_main, c->rgba_read[rgba_ring], 0));
+    }
+    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, c->s_main);
+    c->launches++;
+    if (want_deblock) {
+        launch_deblock_rgba(c->d_pics[slot], n, max_w, max_h, c->s_main);
+        c->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    if (want_rgba) {
+        CU_TRY(cudaEventRecord(c->rgba_written[rgba_ring], c->s_main));
+        c->rgba_parity++;
+    }
+    return 0;
+}
+
+int upload_into(h263cu_ctx* c, h263cu_step* s, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
+                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, cudaStream_t stream) {
+    int e = step_reserve(s, n_mbs, n_units);
+    if (e) return e;
+    s->pics.assign(pics, pics + n_pics);
+    s->n_mbs = n_mbs, s->n_units = n_units;
+    if (n_mbs) CU_TRY(cudaMemcpyAsync(s->d_mbs, mbs, (size_t)n_mbs * sizeof(h263cu_mb), cudaMemcpyHostToDevice, stream));
+    if (n_units)
+        CU_TRY(cudaMemcpyAsync(s->d_events, events, (size_t)n_units * sizeof(h263cu_event), cudaMemcpyHostToDevice, stream));
+    (void)c;
+    return 0;
+}
+
+void free_step_buffers(h263cu_step* s) {
+    if (s->d_mbs) cudaFree(s->d_mbs);
+    if (s->d_events) cudaFree(s->d_events);
+    s->d_mbs = nullptr, s->d_events = nullptr;
+    s->mb_cap = s->ev_cap = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int h263cu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, uint32_t max_height, uint32_t flags,
+                          int* err) {
+    (void)flags;
+    int dummy;
+    if (!err) err = &dummy;
+    *err = 0;
+    if (max_streams == 0 || max_width == 0 || max_height == 0 || max_width > 4080 || max_height > 4080) {
+        *err = H263CU_ERR_BAD_ARGUMENT;
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        *err = H263CU_ERR_NO_DEVICE;
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        *err = H263CU_ERR_NO_DEVICE;
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        *err = H263CU_ERR_CUDA;
+        return nullptr;
+    }
+    h263cu_ctx* c = new (std::nothrow) h263cu_ctx();
+    if (!c) {
+        *err = H263CU_ERR_OUT_OF_MEMORY;
+        return nullptr;
+    }
+    c->device = device;
+    c->max_streams = max_streams, c->max_w = max_width, c->max_h = max_height;
+    c->mbw = (max_width + 15) / 16, c->mbh = (max_height + 15) / 16;
+    // planes are MB-rounded so that whole-macroblock stores never need predication; the
+    // padding is never read as picture content (sample coordinates clamp to the true size)
+    c->pitch_y = c->mbw * 16;
+    c->pitch_c = (uint32_t)round_up(c->mbw * 8, 16);
+    c->rgba_pitch = c->mbw * 16 * 4;
+    c->y_slot = (size_t)c->pitch_y * c->mbh * 16;
+    c->c_slot = (size_t)c->pitch_c * c->mbh * 8;
+    c->rgba_slot = (size_t)c->rgba_pitch * c->mbh * 16;
+    c->streams.resize(max_streams);
+    auto fail = [&](int code) {
+        *err = code;
+        h263cu_destroy(c);
+        return (h263cu_ctx*)nullptr;
+    };
+    const size_t pad = 256;  // aligned-word prediction loads may run a few bytes past a row
+    if (cudaMalloc((void**)&c->y_pool, c->y_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc((void**)&c->cb_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc((void**)&c->cr_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc((void**)&c->rgba_pool, c->rgba_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
+    if (cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    for (int i = 0; i < h263cu_ctx::PIC_RING; i++)
+        if (cudaEventCreateWithFlags(&c->pics_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    for (int i = 0; i < 2; i++) {
+        if (cudaEventCreateWithFlags(&c->ring_h2d_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ring_run_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->rgba_written[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->rgba_read[i], cudaEventDisableTiming) != cudaSuccess)
+            return fail(H263CU_ERR_CUDA);
+    }
+    if (cudaEventCreate(&c->t0) != cudaSuccess || cudaEventCreate(&c->t1) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    // planes start out zeroed (DecodedPicture::new, picture.rs:39-58); every macroblock of a
+    // picture is rewritten by the kernel, so this only matters for defensive reads
+    cudaMemsetAsync(c->y_pool, 0, c->y_slot * 2 * max_streams + pad, c->s_main);
+    cudaMemsetAsync(c->cb_pool, 0, c->c_slot * 2 * max_streams + pad, c->s_main);
+    cudaMemsetAsync(c->cr_pool, 0, c->c_slot * 2 * max_streams + pad, c->s_main);
+    if (cudaStreamSynchronize(c->s_main) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    return c;
+}
+
+void h263cu_destroy(h263cu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->s_main) cudaStreamSynchronize(c->s_main);
+    if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+    if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+    for (int i = 0; i < 2; i++) free_step_buffers(&c->ring[i]);
+    for (int i = 0; i < h263cu_ctx::PIC_RING; i++) {
+        if (c->h_pics[i]) cudaFreeHost(c->h_pics[i]);
+        if (c->d_pics[i]) cudaFree(c->d_pics[i]);
+        if (c->pics_done[i]) cudaEventDestroy(c->pics_done[i]);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (c->ring_h2d_done[i]) cudaEventDestroy(c->ring_h2d_done[i]);
+        if (c->ring_run_done[i]) cudaEventDestroy(c->ring_run_done[i]);
+        if (c->rgba_written[i]) cudaEventDestroy(c->rgba_written[i]);
+        if (c->rgba_read[i]) cudaEventDestroy(c->rgba_read[i]);
+    }
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    if (c->d_jobs) cudaFree(c->d_jobs);
+    if (c->d_sums) cudaFree(c->d_sums);
+    if (c->y_pool) cudaFree(c->y_pool);
+    if (c->cb_pool) cudaFree(c->cb_pool);
+    if (c->cr_pool) cudaFree(c->cr_pool);
+    if (c->rgba_pool) cudaFree(c->rgba_pool);
+    if (c->s_main) cudaStreamDestroy(c->s_main);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+int h263cu_device_of(h263cu_ctx* c) { return c ? c->device : -1; }
+
+void* h263cu_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void h263cu_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+h263cu_step* h263cu_step_upload(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
+                                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, int* err) {
+    int dummy;
+    if (!err) err = &dummy;
+    *err = 0;
+    if (!c || !pics || (!mbs && n_mbs) || (!events && n_units)) {
+        *err = H263CU_ERR_BAD_ARGUMENT;
+        return nullptr;
+    }
+    cudaSetDevice(c->device);
+    h263cu_step* s = new (std::nothrow) h263cu_step();
+    if (!s) {
+        *err = H263CU_ERR_OUT_OF_MEMORY;
+        return nullptr;
+    }
+    int e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_main);
+    if (e) {
+        free_step_buffers(s);
+        delete s;
+        *err = e;
+        return nullptr;
+    }
+    return s;
+}
+
+void h263cu_step_free(h263cu_ctx* c, h263cu_step* s) {
+    if (!s) return;
+    if (c) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->s_main);
+    }
+    free_step_buffers(s);
+    delete s;
+}
+
+int h263cu_step_run(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
+    if (!c || !s) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    return run_step(c, s, out_flags);
+}
+
+static int submit_common(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs, uint32_t n_mbs,
+                         const h263cu_event* events, uint32_t n_units, uint32_t out_flags) {
+    if (!c || !pics || (!mbs && n_mbs) || (!events && n_units)) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    const int slot = c->ring_pos;
+    c->ring_pos ^= 1;
+    h263cu_step* s = &c->ring[slot];
+    // the copy engine may not overwrite side info that a kernel is still reading
+    CU_TRY(cudaStreamWaitEvent(c->s_h2d, c->ring_run_done[slot], 0));
+    if (n_mbs > s->mb_cap || (size_t)n_units + 8 > s->ev_cap) CU_TRY(cudaEventSynchronize(c->ring_run_done[slot]));
+    int e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_h2d);
+    if (e) return e;
+    CU_TRY(cudaEventRecord(c->ring_h2d_done[slot], c->s_h2d));
+    CU_TRY(cudaStreamWaitEvent(c->s_main, c->ring_h2d_done[slot], 0));
+    e = run_step(c, s, out_flags);
+    if (e) return e;
+    CU_TRY(cudaEventRecord(c->ring_run_done[slot], c->s_main));
+    return 0;
+}
+
+int h263cu_submit_step(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs, uint32_t n_mbs,
+                       const h263cu_event* events, uint32_t n_units, uint32_t out_flags) {
+    return submit_common(c, pics, n_pics, mbs, n_mbs, events, n_units, out_flags);
+}
+
+int h263cu_submit_step_readback(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
+                                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, uint32_t out_flags,
+                                uint8_t* host_rgba, const uint64_t* rgba_offsets) {
+    if (!host_rgba) return H263CU_ERR_BAD_ARGUMENT;
+    out_flags |= H263CU_OUT_RGBA;
+    int e = submit_common(c, pics, n_pics, mbs, n_mbs, events, n_units, out_flags);
+    if (e) return e;
+    const int ring = (int)((c->rgba_parity - 1) & 1u);  // the slot run_step just wrote
+    CU_TRY(cudaStreamWaitEvent(c->s_d2h, c->rgba_written[ring], 0));
+    uint64_t off = 0;
+    uint32_t i = 0;
+    while (i < n_pics) {
+        const h263cu_pic& p = pics[i];
+        const uint64_t dst = rgba_offsets ? rgba_offsets[i] : off;
+        const size_t tight = (size_t)p.width * 4;
+        const bool dense = tight == c->rgba_pitch && (size_t)p.height * c->rgba_pitch == c->rgba_slot;
+        if (dense) {
+            // coalesce runs of consecutive streams with contiguous destinations into one copy
+            uint32_t j = i + 1;
+            while (j < n_pics && pics[j].stream == pics[j - 1].stream + 1 && pics[j].width == p.width &&
+                   pics[j].height == p.height &&
+                   (!rgba_offsets || rgba_offsets[j] == rgba_offsets[j - 1] + c->rgba_slot))
+                j++;
+            CU_TRY(cudaMemcpyAsync(host_rgba + dst, c->rgba(p.stream, ring), (size_t)(j - i) * c->rgba_slot,
+                                   cudaMemcpyDeviceToHost, c->s_d2h));
+            off = dst + (uint64_t)(j - i) * c->rgba_slot;
+            i = j;
+        } else {
+            CU_TRY(cudaMemcpy2DAsync(host_rgba + dst, tight, c->rgba(p.stream, ring), c->rgba_pitch, tight, p.height,
+                                     cudaMemcpyDeviceToHost, c->s_d2h));
+            off = dst + (uint64_t)tight * p.height;
+            i++;
+        }
+    }
+    CU_TRY(cudaEventRecord(c->rgba_read[ring], c->s_d2h));
+    return 0;
+}
+
+int h263cu_sync(h263cu_ctx* c) {
+    if (!c) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    CU_TRY(cudaStreamSynchronize(c->s_h2d));
+    CU_TRY(cudaStreamSynchronize(c->s_main));
+    CU_TRY(cudaStreamSynchronize(c->s_d2h));
+    return 0;
+}
+
+int h263cu_stream_info(h263cu_ctx* c, uint32_t stream, uint32_t* width, uint32_t* height, uint32_t* pic_type,
+                       uint32_t* pquant, uint32_t* temporal_reference) {
+    if (!c || stream >= c->max_streams) return H263CU_ERR_BAD_ARGUMENT;
+    const StreamState& st = c->streams[stream];
+    if (!st.has_pic) return H263CU_ERR_NO_PICTURE;
+    if (width) *width = st.w;
+    if (height) *height = st.h;
+    if (pic_type) *pic_type = st.pic_type;
+    if (pquant) *pquant = st.pquant;
+    if (temporal_reference) *temporal_reference = st.tr;
+    return 0;
+}
+
+int h263cu_read_yuv(h263cu_ctx* c, uint32_t stream, uint8_t* y, uint8_t* cb, uint8_t* cr) {
+    if (!c || stream >= c->max_streams || !y || !cb || !cr) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    const StreamState& st = c->streams[stream];
+    if (!st.has_pic) return H263CU_ERR_NO_PICTURE;
+    CU_TRY(cudaStreamSynchronize(c->s_main));
+    const size_t cw = (st.w + 1) / 2, ch = (st.h + 1) / 2;
+    CU_TRY(cudaMemcpy2D(y, st.w, c->plane(0, stream, st.cur_slot), c->pitch_y, st.w, st.h, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy2D(cb, cw, c->plane(1, stream, st.cur_slot), c->pitch_c, cw, ch, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy2D(cr, cw, c->plane(2, stream, st.cur_slot), c->pitch_c, cw, ch, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int h263cu_read_rgba(h263cu_ctx* c, uint32_t stream, uint8_t* rgba) {
+    if (!c || stream >= c->max_streams || !rgba) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    const StreamState& st = c->streams[stream];
+    if (!st.has_pic || st.rgba_slot < 0) return H263CU_ERR_NO_PICTURE;
+    CU_TRY(cudaStreamSynchronize(c->s_main));
+    CU_TRY(cudaMemcpy2D(rgba, (size_t)st.w * 4, c->rgba(stream, st.rgba_slot), c->rgba_pitch, (size_t)st.w * 4, st.h,
+                        cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int h263cu_checksums(h263cu_ctx* c, const uint32_t* streams, uint32_t n, uint64_t* out4) {
+    if (!c || !streams || !out4) return H263CU_ERR_BAD_ARGUMENT;
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    std::vector<ChecksumJob> jobs;
+    jobs.reserve((size_t)n * 4);
+    for (uint32_t i = 0; i < n; i++) {
+        if (streams[i] >= c->max_streams) return H263CU_ERR_BAD_ARGUMENT;
+        const StreamState& st = c->streams[streams[i]];
+        if (!st.has_pic) return H263CU_ERR_NO_PICTURE;
+        const uint32_t cw = (st.w + 1u) / 2u, ch = (st.h + 1u) / 2u;
+        jobs.push_back({c->plane(0, streams[i], st.cur_slot), st.w, st.h, c->pitch_y, i * 4 + 0});
+        jobs.push_back({c->plane(1, streams[i], st.cur_slot), cw, ch, c->pitch_c, i * 4 + 1});
+        jobs.push_back({c->plane(2, streams[i], st.cur_slot), cw, ch, c->pitch_c, i * 4 + 2});
+        if (st.rgba_slot >= 0)
+            jobs.push_back({c->rgba(streams[i], st.rgba_slot), (uint32_t)st.w * 4u, st.h, c->rgba_pitch, i * 4 + 3});
+    }
+    if (jobs.size() > c->jobs_cap) {
+        if (c->d_jobs) cudaFree(c->d_jobs);
+        if (c->d_sums) cudaFree(c->d_sums);
+        c->d_jobs = nullptr, c->d_sums = nullptr;
+        c->jobs_cap = 0;
+        const size_t cap = (size_t)n * 4 + 64;
+        CU_TRY(cudaMalloc((void**)&c->d_jobs, cap * sizeof(ChecksumJob)));
+        CU_TRY(cudaMalloc((void**)&c->d_sums, cap * sizeof(unsigned long long)));
+        c->jobs_cap = cap;
+    }
+    CU_TRY(cudaMemcpyAsync(c->d_jobs, jobs.data(), jobs.size() * sizeof(ChecksumJob), cudaMemcpyHostToDevice, c->s_main));
+    CU_TRY(cudaMemsetAsync(c->d_sums, 0, (size_t)n * 4 * sizeof(unsigned long long), c->s_main));
+    // grid.y is limited to 65535 jobs per launch
+    for (size_t first = 0; first < jobs.size(); first += 60000) {
+        const uint32_t cnt = (uint32_t)std::min<size_t>(60000, jobs.size() - first);
+        launch_checksums(c->d_jobs + first, cnt, c->d_sums, c->s_main);
+        c->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out4, c->d_sums, (size_t)n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_main));
+    CU_TRY(cudaStreamSynchronize(c->s_main));
+    return 0;
+}
+
+int h263cu_timer_start(h263cu_ctx* c) {
+    if (!c) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    CU_TRY(cudaEventRecord(c->t0, c->s_main));
+    return 0;
+}
+int h263cu_timer_stop(h263cu_ctx* c, float* ms) {
+    if (!c || !ms) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    CU_TRY(cudaEventRecord(c->t1, c->s_main));
+    CU_TRY(cudaEventSynchronize(c->t1));
+    CU_TRY(cudaEventElapsedTime(ms, c->t0, c->t1));
+    return 0;
+}
+uint64_t h263cu_launch_count(h263cu_ctx* c) { return c ? c->launches : 0; }
+
+// ---- stateless drop-ins: host buffers in, host buffers out ---------------------------------
+static std::mutex g_scratch_mutex;
+static uint8_t* g_scratch = nullptr;
+static size_t g_scratch_cap = 0;
+
+static int scratch_reserve(size_t bytes) {
+    if (bytes <= g_scratch_cap) return 0;
+    if (g_scratch) cudaFree(g_scratch);
+    g_scratch = nullptr;
+    g_scratch_cap = 0;
+    CU_TRY(cudaMalloc((void**)&g_scratch, bytes));
+    g_scratch_cap = bytes;
+    return 0;
+}
+
+int h263cu_yuv420_to_rgba(const uint8_t* y, const uint8_t* chroma_b, const uint8_t* chroma_r, size_t y_len,
+                          size_t y_width, uint8_t* rgba_out) {
+    if (y_len == 0) return 0;  // bt601.rs:106-112
+    if (!y || !chroma_b || !chroma_r || !rgba_out || y_width == 0 || y_len % y_width != 0 || y_width > 65535)
+        return H263CU_ERR_BAD_ARGUMENT;
+    if (h263cu_device_count() == 0) return H263CU_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    const size_t h = y_len / y_width, cw = (y_width + 1) / 2, ch = (h + 1) / 2, clen = cw * ch;
+    const size_t o_cb = round_up(y_len, 256), o_cr = o_cb + round_up(clen, 256), o_out = o_cr + round_up(clen, 256);
+    int e = scratch_reserve(o_out + y_len * 4);
+    if (e) return e;
+    CU_TRY(cudaMemcpy(g_scratch, y, y_len, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g_scratch + o_cb, chroma_b, clen, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g_scratch + o_cr, chroma_r, clen, cudaMemcpyHostToDevice));
+    launch_yuv420_to_rgba(g_scratch, g_scratch + o_cb, g_scratch + o_cr, (uint32_t)y_width, (uint32_t)h, g_scratch + o_out, 0);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(rgba_out, g_scratch + o_out, y_len * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int h263cu_deblock(const uint8_t* data, size_t len, size_t width, uint8_t strength, uint8_t* out) {
+    if (len == 0) return 0;
+    if (!data || !out || width == 0 || len % width != 0 || width > 65535) return H263CU_ERR_BAD_ARGUMENT;
+    if (h263cu_device_count() == 0) return H263CU_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    const size_t h = len / width;
+    const size_t o_out = round_up(len, 256);
+    int e = scratch_reserve(o_out + len);
+    if (e) return e;
+    CU_TRY(cudaMemcpy(g_scratch, data, len, cudaMemcpyHostToDevice));
+    launch_deblock_plane(g_scratch, g_scratch + o_out, (uint32_t)width, (uint32_t)h, strength, 0);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, g_scratch + o_out, len, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// kernels.cuh -- device-side data structures and launch wrappers shared by kernels.cu
+// and context.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/h263cu.h"
+
+namespace h263dev {
+
+// Device-side picture descriptor, built by the host for every picture of a step when the
+// step is run (plane slots toggle per stream, so pointers are only known then).
+struct PicDev {
+    uint8_t* cur[3];        // Y, Cb, Cr planes being reconstructed
+    const uint8_t* ref[3];  // reference planes (previous picture of the stream); may be null
+    uint8_t* rgba;          // RGBA output (null when not requested)
+    uint32_t first_event;   // offset of the picture's events in the step's event array
+    uint32_t rgba_pitch;    // bytes
+    uint16_t w, h;          // true luma dimensions
+    uint16_t cw, ch;        // true chroma dimensions = ceil(w/2), ceil(h/2)
+    uint16_t pitch_y, pitch_c;
+    uint8_t strength;       // QUANT_TO_STRENGTH[pquant]
+    uint8_t flags;
+    uint8_t pad[2];
+};
+
+// Fused reconstruction of every macroblock of a step: inverse RLE + dequant + classify +
+// IDCT + motion compensation + add/clamp -> planes, and BT.601 RGBA when `emit_rgba`.
+void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
+                  int emit_rgba, cudaStream_t stream);
+
+// Deblocking post-filter (per plane, per picture) fused with the RGBA conversion.
+// grid = (max tiles per picture, n_pics).
+void launch_deblock_rgba(const PicDev* pics, uint32_t n_pics, uint32_t max_w, uint32_t max_h, cudaStream_t stream);
+
+// Stateless kernels behind h263cu_yuv420_to_rgba / h263cu_deblock (tight planes).
+void launch_yuv420_to_rgba(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, uint32_t w, uint32_t h,
+                           uint8_t* rgba, cudaStream_t stream);
+void launch_deblock_plane(const uint8_t* in, uint8_t* out, uint32_t w, uint32_t h, int strength, cudaStream_t stream);
+
+// Position-weighted checksums of the tight w x h window of a pitched plane:
+// out[k] += sum_i (byte[i]+1) * ((uint32)(i*2654435761) | 1), i = y*row_bytes + x.
+struct ChecksumJob {
+    const uint8_t* base;
+    uint32_t row_bytes;  // bytes per row that count
+    uint32_t rows;
+    uint32_t pitch;
+    uint32_t out_index;
+};
+void launch_checksums(const ChecksumJob* jobs, uint32_t n_jobs, unsigned long long* out, cudaStream_t stream);
+
+}  // namespace h263dev

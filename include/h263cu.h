@@ -1,0 +1,276 @@
+/*
+ * h263cu.h -- C ABI of libh263cu.so, the B200-native reconstruction path for
+ * ruffle-rs/h263-rs streams (H.263 / Sorenson Spark).
+ *
+ * The reference is a pure-Rust library without an FFI layer; the boundary it offers is
+ * its public Rust API.  Each entry point below names the reference interface it stands
+ * in for (paths relative to the reference repository).  A Rust `-sys` crate binds these
+ * symbols 1:1; the façade crates on top keep the reference's own
+ * names (`H263State::decode_next_picture`, `yuv::bt601::yuv420_to_rgba`,
+ * `deblock::deblock::deblock`).
+ *
+ * Division of labour (BASELINE.json north_star):
+ *   host  : serial bitstream / VLC parse, one parser per stream, threaded across streams
+ *           (h263cu_parser_*, h263cu_parse_step).  Output = compact side info:
+ *           h263cu_pic + h263cu_mb records + 16-bit run/level event units.
+ *   device: everything after the parse -- inverse RLE + dequantisation, block
+ *           classification, f32 IDCT (reference operation order, no FMA), motion
+ *           compensation with edge clamping, residual add + clamp, optional deblocking
+ *           post-filter, BT.601 YUV420 -> RGBA.  (h263cu_step_*, h263cu_submit_step)
+ * There is no CPU fallback: device entry points fail with H263CU_ERR_NO_DEVICE /
+ * H263CU_ERR_CUDA when no usable GPU is present.
+ *
+ * Threading: a context is externally synchronised (one submitting thread per context);
+ * parsers are independent objects; h263cu_parse_step runs its own worker threads.
+ * Ownership: the caller owns every host buffer; the context owns all device memory.
+ * Errors: 0 = success, negative = failure, never aborts.
+ */
+#ifndef H263CU_H
+#define H263CU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes --------------------------------------------------------------------
+ * -1..-17 are the reference's h263::Error variants in declaration order
+ * (h263/src/error.rs:6-57). */
+#define H263CU_OK 0
+#define H263CU_ERR_INTERNAL_DECODER_ERROR (-1)
+#define H263CU_ERR_MIDDLE_OF_BITSTREAM (-2)
+#define H263CU_ERR_INVALID_MACROBLOCK_HEADER (-3)
+#define H263CU_ERR_INVALID_MACROBLOCK_CODED_BITS (-4)
+#define H263CU_ERR_INVALID_INTRA_DC (-5)
+#define H263CU_ERR_INVALID_SHORT_COEFFICIENT (-6)
+#define H263CU_ERR_INVALID_LONG_COEFFICIENT (-7)
+#define H263CU_ERR_INVALID_MVD (-8)
+#define H263CU_ERR_INVALID_PTYPE (-9)
+#define H263CU_ERR_INVALID_PLUSPTYPE (-10)
+#define H263CU_ERR_INVALID_GOB_HEADER (-11)
+#define H263CU_ERR_INVALID_BITSTREAM (-12)
+#define H263CU_ERR_PICTURE_FORMAT_MISSING (-13)
+#define H263CU_ERR_PICTURE_FORMAT_INVALID (-14)
+#define H263CU_ERR_UNCODED_IFRAME_BLOCKS (-15)
+#define H263CU_ERR_UNHANDLED_IO_ERROR (-16) /* in-memory packets: UnexpectedEof */
+#define H263CU_ERR_UNIMPLEMENTED_DECODING (-17)
+/* library errors */
+#define H263CU_ERR_BAD_ARGUMENT (-100)
+#define H263CU_ERR_CUDA (-101)
+#define H263CU_ERR_NO_DEVICE (-102)
+#define H263CU_ERR_CAPACITY (-103)              /* stream / MB / event capacity exceeded */
+#define H263CU_ERR_REFERENCE_WOULD_ABORT (-104) /* input on which the reference panics (abort) */
+#define H263CU_ERR_NO_PICTURE (-105)            /* stream has not decoded a picture yet */
+#define H263CU_ERR_OUT_OF_MEMORY (-106)
+
+/* error.rs:66-93 classification helpers */
+int h263cu_is_eof_error(int err);
+int h263cu_is_macroblock_error(int err);
+int h263cu_is_gob_error(int err);
+const char* h263cu_strerror(int err);
+int h263cu_version(void);
+
+/* DecoderOption (h263/src/decoder/types.rs:3-18) */
+#define H263CU_OPT_SORENSON_SPARK_BITSTREAM 1u
+#define H263CU_OPT_USE_SCALABILITY_MODE 2u
+
+/* ---- side-info format (host -> device) ------------------------------------------------
+ * One time step = one picture for each of n streams.  All three arrays live in
+ * caller-owned (ideally pinned) memory. */
+
+#define H263CU_PIC_I 0
+#define H263CU_PIC_P 1
+#define H263CU_PIC_DISPOSABLE_P 2
+#define H263CU_PIC_OTHER 3 /* PB / reserved types: only all-uncoded pictures decode */
+
+#define H263CU_PICFLAG_DEBLOCK 1u   /* Sorenson DeblockingFlag (advisory, picture.rs:319-325) */
+#define H263CU_PICFLAG_HAS_INTER 2u /* at least one MB needs the reference picture */
+
+typedef struct h263cu_pic { /* 32 bytes */
+    uint32_t stream;        /* stream slot inside the context, < max_streams */
+    uint16_t width, height; /* true luma dimensions (not MB rounded) */
+    uint8_t mb_w, mb_h;     /* ceil(width/16), ceil(height/16) (state.rs:173-174); <= 255 */
+    uint8_t pic_type;       /* H263CU_PIC_* */
+    uint8_t pquant;         /* PQUANT of the header; selects the deblock strength */
+    uint8_t flags;          /* H263CU_PICFLAG_* */
+    uint8_t version;        /* Sorenson version field (0xFF for baseline H.263) */
+    uint16_t temporal_reference;
+    uint32_t first_mb;      /* index of the picture's first record in the step's mb array */
+    uint32_t n_mbs;         /* mb_w * mb_h */
+    uint32_t first_event;   /* index of the picture's first unit in the step's event array */
+    uint32_t n_event_units; /* 16-bit units used by this picture */
+} h263cu_pic;
+
+#define H263CU_MB_INTER 1u  /* motion compensated from the reference (MacroblockType::is_inter) */
+#define H263CU_MB_WIDE 2u   /* this MB's events use the 2-unit wide form */
+#define H263CU_MB_FOURMV 4u /* four motion vectors (informational; mv[] always holds 4) */
+#define H263CU_MB_CODED 8u  /* COD=0 (informational) */
+
+typedef struct h263cu_mb { /* 24 bytes, raster order inside a picture */
+    uint32_t ev_off;       /* first event unit of the MB, relative to pic.first_event */
+    uint16_t pic;          /* index into the step's pic array */
+    uint8_t mbx, mby;      /* macroblock coordinates */
+    uint8_t flags;         /* H263CU_MB_* */
+    uint8_t quant;         /* in-force quantiser 1..31 (state.rs:226-227) */
+    uint8_t nev[6];        /* events per block, order Y0 Y1 Y2 Y3 Cb Cr (state.rs:287-381) */
+    union {
+        int8_t mv[4][2];    /* INTER: decoded half-pel vectors (x, y) per luma block */
+        uint8_t intradc[6]; /* INTRA: raw 8-bit INTRADC codes (0xFF => 1024, else code*8);
+                               0 = block dropped (zig-zag overflow, rle.rs:125-127) */
+    } u;
+} h263cu_mb;
+
+/* Event unit, narrow form (default): bits 15..10 = RUN, bits 9..0 = LEVEL as a signed
+ * 10-bit integer (never 0).  Wide form (H263CU_MB_WIDE, needed when some |LEVEL| of the MB
+ * exceeds the 10-bit range, i.e. Sorenson 11-bit escapes): two units per event, first =
+ * RUN, second = LEVEL as int16.  The device accumulates RUN into zig-zag positions,
+ * dequantises and classifies (rle.rs:82-172).  Precondition: the events of one block
+ * never push the zig-zag index past 63 (the front end drops such blocks, as the
+ * reference does). */
+typedef uint16_t h263cu_event;
+
+/* ---- host front end (replaces H263Reader + the serial loop of
+ *      H263State::decode_next_picture, h263/src/decoder/state.rs:142-427) ---------------- */
+typedef struct h263cu_parser h263cu_parser;
+
+/* H263State::new (state.rs:42-50): one parser per stream */
+h263cu_parser* h263cu_parser_create(uint32_t decoder_options);
+void h263cu_parser_destroy(h263cu_parser*);
+/* Seek: discard all stream state; the next picture must be an I picture (state.rs:134-137) */
+void h263cu_parser_reset(h263cu_parser*);
+
+/* H263State::parse_picture (state.rs:102-111): header only; fills width/height/mb_w/mb_h/
+ * pic_type/pquant/flags/version/temporal_reference/n_mbs of *pic. Stateless. */
+int h263cu_peek_picture(uint32_t decoder_options, const uint8_t* data, size_t len, h263cu_pic* pic);
+
+/* Serial parse of one packet = one picture (one H263Reader::from_source(&packet[..]) per
+ * picture).  Writes *pic, pic->n_mbs records to mbs[0..] and the event units to events[0..];
+ * pic->first_mb / first_event are set to mb_base / ev_base and every record's `pic` field
+ * to pic_index, so that many pictures can be packed into one step.  Transactional like the
+ * reference (state.rs:120-137): on error the parser state is unchanged. */
+int h263cu_parse_picture(h263cu_parser*, const uint8_t* data, size_t len, uint32_t stream,
+                         uint16_t pic_index, uint32_t mb_base, uint32_t ev_base, h263cu_pic* pic,
+                         h263cu_mb* mbs, uint32_t mb_cap, h263cu_event* events, uint32_t ev_cap);
+
+/* Threaded parse of one time step: packet i belongs to parsers[i] / stream_ids[i] and
+ * becomes picture i.  Pictures that fail to parse are reported in per_pic_err[i] (may be
+ * NULL) and left out of the step (the remaining pictures are packed densely; *n_pics_out
+ * counts them and pic_of_input[i] (may be NULL) gives the packed index or -1).
+ * `threads` <= 0 selects std::thread::hardware_concurrency(). */
+int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                      const uint32_t* stream_ids, uint32_t n, int threads, h263cu_pic* pics,
+                      h263cu_mb* mbs, uint32_t mb_cap, h263cu_event* events, uint32_t ev_cap,
+                      uint32_t* n_pics_out, uint32_t* n_mbs_out, uint32_t* n_units_out,
+                      int* per_pic_err, int32_t* pic_of_input);
+
+/* ---- device context ---------------------------------------------------------------- */
+typedef struct h263cu_ctx h263cu_ctx;
+typedef struct h263cu_step h263cu_step;
+
+#define H263CU_OUT_RGBA 1u    /* produce RGBA (yuv::bt601::yuv420_to_rgba) for every picture */
+#define H263CU_OUT_DEBLOCK 2u /* RGBA from deblocked planes: deblock::deblock(plane, width,
+                                 QUANT_TO_STRENGTH[pquant]) per plane; the reference frames
+                                 stay un-deblocked (deblock/src/lib.rs:1-2) */
+
+int h263cu_device_count(void);
+/* Device memory for max_streams streams of up to max_width x max_height: two
+ * reconstruction slots (current / reference) and two RGBA slots per stream. */
+h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, uint32_t max_height,
+                          uint32_t flags, int* err);
+void h263cu_destroy(h263cu_ctx*);
+int h263cu_device_of(h263cu_ctx*);
+
+/* Pinned host memory for side info / read-back buffers (cudaHostAlloc). */
+void* h263cu_alloc_pinned(size_t bytes);
+void h263cu_free_pinned(void* p);
+
+/* Copy one step's side info into device memory (cudaMemcpyAsync on the context stream) and
+ * keep it there: the "inputs resident in HBM" form used for kernel-only timing. */
+h263cu_step* h263cu_step_upload(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
+                                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, int* err);
+void h263cu_step_free(h263cu_ctx*, h263cu_step*);
+/* Reconstruct every picture of the step (async): the recon tail of decode_next_picture
+ * (state.rs:419-485: gather + 3x idct_channel + reference bookkeeping) followed by the
+ * requested outputs.  Each stream's "last picture" becomes the reference of its next one
+ * (state.rs:72-78). */
+int h263cu_step_run(h263cu_ctx*, h263cu_step*, uint32_t out_flags);
+/* upload + run through an internal double-buffered ring (the streaming form) */
+int h263cu_submit_step(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
+                       uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, uint32_t out_flags);
+/* submit_step + asynchronous read-back of the RGBA pictures of this step into
+ * host_rgba (pinned; picture i at i * 4*width*height when all pictures share one size,
+ * else at rgba_offsets[i]); overlaps the copy with the next step's kernels.  Call
+ * h263cu_sync before reading host_rgba. */
+int h263cu_submit_step_readback(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
+                                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units,
+                                uint32_t out_flags, uint8_t* host_rgba, const uint64_t* rgba_offsets);
+int h263cu_sync(h263cu_ctx*);
+
+/* DecodedPicture accessors (h263/src/decoder/picture.rs:60-142): tight row-major planes,
+ * chroma = ceil(w/2) x ceil(h/2).  Synchronise the context first. */
+int h263cu_stream_info(h263cu_ctx*, uint32_t stream, uint32_t* width, uint32_t* height, uint32_t* pic_type,
+                       uint32_t* pquant, uint32_t* temporal_reference);
+int h263cu_read_yuv(h263cu_ctx*, uint32_t stream, uint8_t* y, uint8_t* cb, uint8_t* cr);
+/* RGBA of the stream's last picture (4*width*height bytes, R,G,B,A); requires that the
+ * last step ran with H263CU_OUT_RGBA. */
+int h263cu_read_rgba(h263cu_ctx*, uint32_t stream, uint8_t* rgba);
+/* Position-weighted 64-bit checksums computed on the device over the tight planes /
+ * RGBA of the last picture of each listed stream:
+ *   sum_i (byte[i] + 1) * ((uint32)(i * 2654435761) | 1)   (mod 2^64)
+ * out = n x {y, cb, cr, rgba}. */
+int h263cu_checksums(h263cu_ctx*, const uint32_t* streams, uint32_t n, uint64_t* out4);
+
+/* CUDA-event timing on the context stream (used by bench.py). */
+int h263cu_timer_start(h263cu_ctx*);
+int h263cu_timer_stop(h263cu_ctx*, float* milliseconds);
+/* Number of kernel launches issued by this context so far. */
+uint64_t h263cu_launch_count(h263cu_ctx*);
+
+/* ---- stateless drop-ins for the sibling crates (host buffers in, host buffers out) ---- */
+/* yuv::bt601::yuv420_to_rgba(y, chroma_b, chroma_r, y_width) -> Vec<u8>
+ * (yuv/src/bt601.rs:105-196).  rgba_out holds 4*y_len bytes. y_len == 0 is a no-op. */
+int h263cu_yuv420_to_rgba(const uint8_t* y, const uint8_t* chroma_b, const uint8_t* chroma_r, size_t y_len,
+                          size_t y_width, uint8_t* rgba_out);
+/* deblock::deblock::deblock(data, width, strength) -> Vec<u8> (deblock/src/deblock.rs:305-315) */
+int h263cu_deblock(const uint8_t* data, size_t len, size_t width, uint8_t strength, uint8_t* out);
+/* deblock::deblock::QUANT_TO_STRENGTH (deblock/src/deblock.rs:5-8) */
+extern const uint8_t h263cu_quant_to_strength[32];
+
+/* ---- synthetic Sorenson-flavour bitstream generator (the repo has no encoder) ---------- */
+typedef struct h263cu_synth_params {
+    uint32_t width, height;
+    uint32_t n_pictures;
+    uint64_t seed;
+    uint32_t flavour;      /* 0 = Sorenson Spark, 1 = baseline H.263 (standard sizes only) */
+    uint32_t version;      /* Sorenson version field: 0 or 1 (1 = 7/11-bit escapes) */
+    uint32_t intra_period; /* an I picture every N pictures; 0 = only the first */
+    uint32_t deblock_flag; /* value of the Sorenson DeblockingFlag */
+    uint32_t qp_min, qp_max;
+    uint32_t pct_uncoded;  /* P pictures: % of MBs with COD=1 */
+    uint32_t pct_intra;    /* P pictures: % of MBs coded INTRA */
+    uint32_t pct_fourmv;   /* P pictures: % of MBs coded INTER4V */
+    uint32_t pct_dquant;   /* % of coded MBs carrying DQUANT */
+    uint32_t pct_cbp_inter; /* % of blocks of an inter MB that carry coefficients */
+    uint32_t pct_cbp_intra; /* % of blocks of an intra MB that carry AC coefficients */
+    uint32_t mean_events_x10; /* mean TCOEF events per coded block, times 10 */
+    uint32_t pct_escape;   /* % of events forced through the ESCAPE path */
+    uint32_t permille_overflow; /* per-mille of coded blocks whose runs overflow the zig-zag */
+    uint32_t mv_mode;      /* 0 small vectors, 1 full range uniform, 2 biased across borders */
+    uint32_t truncate_permille; /* per-mille of P pictures that end early (padding path) */
+    uint32_t reserved[4];
+} h263cu_synth_params;
+
+void h263cu_synth_default_params(h263cu_synth_params* p, uint32_t width, uint32_t height, uint32_t n_pictures,
+                                 uint64_t seed);
+/* Writes the stream's packets back to back into out (one byte-aligned, zero-padded packet
+ * per picture) and their offsets/lengths; returns the number of bytes needed (call with
+ * cap = 0 to size the buffer) or a negative error. */
+int64_t h263cu_synth_stream(const h263cu_synth_params* p, uint8_t* out, size_t cap, uint64_t* pkt_off,
+                            uint32_t* pkt_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H263CU_H */

@@ -1,0 +1,100 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+import oracle_lib as O
+from h263_rs_b200 import _lib, frontend, synth
+
+INTER_TYPES = (0, 1, 2, 5)
+
+
+def oracle_decode_stream(packets, options=1, deblock=False):
+    """Reference path on the CPU: decode -> [deblock] -> RGBA, per picture.
+    Returns a list of dicts (or the error code for pictures that fail)."""
+    st = O.OracleState(options)
+    out = []
+    for pk in packets:
+        try:
+            st.decode_next_picture(pk)
+        except O.OracleError as e:
+            out.append(e.code)
+            continue
+        info = st.info()
+        y, cb, cr = st.yuv()
+        w = info["width"]
+        cw = (w + 1) // 2
+        if deblock:
+            s = O.lib().orc_quant_to_strength(info["quant"])
+            dy, dcb, dcr = O.deblock(y, w, s), O.deblock(cb, cw, s), O.deblock(cr, cw, s)
+            rgba = O.yuv420_to_rgba(dy, dcb, dcr, w)
+        else:
+            rgba = O.yuv420_to_rgba(y, cb, cr, w)
+        out.append(dict(info=info, y=y, cb=cb, cr=cr, rgba=rgba))
+    return out
+
+
+def weighted_sum(a):
+    a = np.ascontiguousarray(a, np.uint8).reshape(-1).astype(np.uint64)
+    i = np.arange(a.size, dtype=np.uint64)
+    w = ((i * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) | np.uint64(1)
+    with np.errstate(over="ignore"):
+        return int(((a + np.uint64(1)) * w).sum(dtype=np.uint64))
+
+
+def compare_parse_with_oracle(packets, options=1):
+    """Product parser vs oracle parse trace, picture by picture. Returns (#mbs, #events, #errors)."""
+    st = O.OracleState(options, trace=True)
+    ps = frontend.Parser(options)
+    nmb = nev = nerr = 0
+    for i, p in enumerate(packets):
+        oerr = perr = 0
+        try:
+            st.decode_next_picture(p)
+        except O.OracleError as e:
+            oerr = e.code
+        try:
+            pic, mbs, ev = ps.parse_picture(p)
+        except _lib.H263Error as e:
+            perr = -e.code
+        if oerr == 100:
+            assert perr == 104, (i, oerr, perr)
+        else:
+            assert oerr == perr, (i, oerr, perr)
+        if oerr:
+            nerr += 1
+            continue
+        t = st.trace()
+        info = st.info()
+        assert (info["width"], info["height"], info["quant"], info["tr"]) == (
+            pic["width"][0], pic["height"][0], pic["pquant"][0], pic["temporal_reference"][0])
+        assert len(mbs) == len(t["mb_type"])
+        eoff = 0
+        for k in range(len(mbs)):
+            m = mbs[k]
+            inter = t["mb_type"][k] in INTER_TYPES
+            assert bool(m["flags"] & 1) == inter, (i, k)
+            if t["coded"][k]:
+                assert m["quant"] == t["quant"][k], (i, k)
+            if inter:
+                assert np.array_equal(m["u"].view(np.int8).reshape(4, 2), t["mv"][k]), (i, k)
+            blocks = frontend.decode_events(m, ev)
+            for b in range(6):
+                ne = int(t["nev"][k][b])
+                runs, lv = t["run"][eoff : eoff + ne], t["level"][eoff : eoff + ne]
+                eoff += ne
+                idx = 0 if inter else 1
+                ovf = False
+                for r in runs:
+                    idx += int(r)
+                    ovf |= idx >= 64
+                    idx += 1
+                if ovf:  # dropped block (rle.rs:125-127)
+                    assert blocks[b] == []
+                    if not inter:
+                        assert m["u"][b] == 0
+                else:
+                    assert blocks[b] == [(int(a), int(c)) for a, c in zip(runs, lv)], (i, k, b)
+                    if not inter:
+                        assert m["u"][b] == t["intradc"][k][b]
+                nev += ne
+        nmb += len(mbs)
+    return nmb, nev, nerr
