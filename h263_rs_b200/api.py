@@ -180,6 +180,15 @@ class Context:
     def launch_count(self):
         return int(self.L.h263cu_launch_count(self.h))
 
+    def profile_enable(self, on=True):
+        check(self.L.h263cu_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        ms = (C.c_double * 2)()
+        n = (C.c_uint64 * 2)()
+        check(self.L.h263cu_profile_read(self.h, ms, n))
+        return dict(recon_ms=ms[0], recon_launches=int(n[0]), deblock_ms=ms[1], deblock_launches=int(n[1]))
+
 
 class H263State:
     """Mirror of h263::H263State for ONE stream: host parse + GPU reconstruction.

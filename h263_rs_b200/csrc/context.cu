@@ -89,6 +89,14 @@ struct h263cu_ctx {
     // timing
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     uint64_t launches = 0;
+    // optional per-kernel timing (h263cu_profile_*): event pairs, kind 0 = recon, 1 = deblock
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_free;
+    struct ProfSpan {
+        cudaEvent_t a, b;
+        int kind;
+    };
+    std::vector<ProfSpan> prof_spans;
     // checksum scratch
     ChecksumJob* d_jobs = nullptr;
     unsigned long long* d_sums = nullptr;
@@ -135,6 +143,23 @@ int step_reserve(h263cu_step* s, size_t n_mbs, size_t n_units) {
         s->ev_cap = cap;
     }
     return 0;
+}
+
+int prof_begin(h263cu_ctx* c, cudaEvent_t* a, cudaEvent_t* b) {
+    for (cudaEvent_t* e : {a, b}) {
+        if (!c->prof_free.empty()) {
+            *e = c->prof_free.back();
+            c->prof_free.pop_back();
+        } else {
+            CU_TRY(cudaEventCreate(e));
+        }
+    }
+    CU_TRY(cudaEventRecord(*a, c->s_main));
+    return 0;
+}
+void prof_end(h263cu_ctx* c, cudaEvent_t a, cudaEvent_t b, int kind) {
+    cudaEventRecord(b, c->s_main);
+    c->prof_spans.push_back({a, b, kind});
 }
 
 // Validates a step against the context and the per-stream state, builds the PicDev array,
@@ -207,11 +232,16 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         // do not overwrite an RGBA ring slot that is still being read back
         CU_TRY(cudaStreamWaitEvent(c->s_main, c->rgba_read[rgba_ring], 0));
     }
+    cudaEvent_t pa = nullptr, pb = nullptr;
+    if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
     launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, c->s_main);
     c->launches++;
+    if (c->profiling) prof_end(c, pa, pb, 0);
     if (want_deblock) {
+        if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
         launch_deblock_rgba(c->d_pics[slot], n, max_w, max_h, c->s_main);
         c->launches++;
+        if (c->profiling) prof_end(c, pa, pb, 1);
     }
     CU_TRY(cudaGetLastError());
     if (want_rgba) {
@@ -348,6 +378,11 @@ void h263cu_destroy(h263cu_ctx* c) {
     }
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
+    for (auto& sp : c->prof_spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    for (auto e : c->prof_free) cudaEventDestroy(e);
     if (c->d_jobs) cudaFree(c->d_jobs);
     if (c->d_sums) cudaFree(c->d_sums);
     if (c->y_pool) cudaFree(c->y_pool);
@@ -580,6 +615,29 @@ int h263cu_timer_stop(h263cu_ctx* c, float* ms) {
     return 0;
 }
 uint64_t h263cu_launch_count(h263cu_ctx* c) { return c ? c->launches : 0; }
+
+int h263cu_profile_enable(h263cu_ctx* c, int enable) {
+    if (!c) return H263CU_ERR_BAD_ARGUMENT;
+    c->profiling = enable != 0;
+    return 0;
+}
+int h263cu_profile_read(h263cu_ctx* c, double* ms2, uint64_t* launches2) {
+    if (!c || !ms2 || !launches2) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    CU_TRY(cudaStreamSynchronize(c->s_main));
+    ms2[0] = ms2[1] = 0.0;
+    launches2[0] = launches2[1] = 0;
+    for (const auto& sp : c->prof_spans) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ms2[sp.kind] += ms;
+        launches2[sp.kind]++;
+        c->prof_free.push_back(sp.a);
+        c->prof_free.push_back(sp.b);
+    }
+    c->prof_spans.clear();
+    return 0;
+}
 
 // ---- stateless drop-ins: host buffers in, host buffers out ---------------------------------
 static std::mutex g_scratch_mutex;

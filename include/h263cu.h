@@ -227,6 +227,12 @@ int h263cu_timer_start(h263cu_ctx*);
 int h263cu_timer_stop(h263cu_ctx*, float* milliseconds);
 /* Number of kernel launches issued by this context so far. */
 uint64_t h263cu_launch_count(h263cu_ctx*);
+/* Per-kernel timing: when enabled, every recon / deblock launch is bracketed by CUDA events
+ * on the launching stream.  h263cu_profile_read synchronises, accumulates the elapsed times
+ * since the last read into ms[0] (recon) / ms[1] (deblock+rgba) and the launch counts into
+ * launches[0..1], and resets. */
+int h263cu_profile_enable(h263cu_ctx*, int enable);
+int h263cu_profile_read(h263cu_ctx*, double* ms2, uint64_t* launches2);
 
 /* ---- stateless drop-ins for the sibling crates (host buffers in, host buffers out) ---- */
 /* yuv::bt601::yuv420_to_rgba(y, chroma_b, chroma_r, y_width) -> Vec<u8>

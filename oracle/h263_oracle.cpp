@@ -1681,4 +1681,78 @@ double orc_bench_decode(const uint8_t* blob, const uint64_t* pkt_off, const uint
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+struct orc_batch {
+    std::vector<orc_state> states;
+    uint64_t step_index = 0;
+};
+
+orc_batch* orc_batch_new(int n_streams, int decoder_options) {
+    ensure_trees();
+    orc_batch* b = new orc_batch();
+    b->states.resize((size_t)n_streams);
+    for (auto& s : b->states) s.decoder_options = decoder_options;
+    return b;
+}
+void orc_batch_free(orc_batch* b) { delete b; }
+
+double orc_batch_step(orc_batch* b, const uint8_t* blob, const uint64_t* pkt_off, const uint32_t* pkt_len,
+                      int do_deblock, int threads, uint64_t* pixels, uint64_t* checksum) {
+    const int n = (int)b->states.size();
+    if (threads < 1) threads = 1;
+    if (threads > n) threads = n;
+    std::atomic<int> next{0}, failed{0};
+    std::atomic<uint64_t> px_total{0}, ck_total{0};
+    const uint64_t step_index = b->step_index++;
+    auto worker = [&]() {
+        uint64_t px = 0, ck = 0;
+        std::vector<uint8_t> rgba, dy, dcb, dcr;
+        for (;;) {
+            int s = next.fetch_add(1);
+            if (s >= n) break;
+            orc_state& st = b->states[(size_t)s];
+            Reader r{blob + pkt_off[s], pkt_len[s], 0};
+            Err e = decode_next_picture(&st, r);
+            if (e) {
+                failed.store(e);
+                continue;
+            }
+            const DecodedPicture& p = st.last;
+            rgba.resize(p.luma.size() * 4);
+            if (do_deblock) {
+                int strength = QUANT_TO_STRENGTH[p.header.quantizer & 31];
+                dy.resize(p.luma.size());
+                dcb.resize(p.chroma_b.size());
+                dcr.resize(p.chroma_r.size());
+                deblock(p.luma.data(), p.luma.size(), (size_t)p.w, strength, dy.data());
+                deblock(p.chroma_b.data(), p.chroma_b.size(), p.chroma_samples_per_row, strength, dcb.data());
+                deblock(p.chroma_r.data(), p.chroma_r.size(), p.chroma_samples_per_row, strength, dcr.data());
+                yuv420_to_rgba(dy.data(), dcb.data(), dcr.data(), dy.size(), (size_t)p.w, rgba.data());
+            } else {
+                yuv420_to_rgba(p.luma.data(), p.chroma_b.data(), p.chroma_r.data(), p.luma.size(), (size_t)p.w,
+                               rgba.data());
+            }
+            px += p.luma.size();
+            uint64_t pid = ((uint64_t)s << 20) + step_index;
+            ck += weighted_sum(rgba.data(), rgba.size()) * ((0x9E3779B97F4A7C15ull * (pid + 1)) | 1ull);
+        }
+        px_total.fetch_add(px);
+        ck_total.fetch_add(ck);
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    auto t1 = std::chrono::steady_clock::now();
+    if (failed.load()) return -(double)failed.load();
+    if (pixels) *pixels += px_total.load();
+    if (checksum) *checksum += ck_total.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int orc_batch_stream_yuv(orc_batch* b, int s, uint8_t* y, uint8_t* cb, uint8_t* cr) {
+    if (s < 0 || s >= (int)b->states.size()) return -1;
+    return orc_last_picture_yuv(&b->states[(size_t)s], y, cb, cr);
+}
+
 }  // extern "C"

@@ -142,6 +142,18 @@ double orc_bench_decode(const uint8_t* blob, const uint64_t* pkt_off, const uint
                         const uint32_t* pic_first, int n_streams, int decoder_options,
                         int do_deblock, int threads, uint64_t* pixels, uint64_t* checksum);
 
+/* Step-wise form of the same baseline: n_streams persistent H263States; one call decodes
+ * ONE picture for every stream (packet s = blob + pkt_off[s], pkt_len[s]) on `threads`
+ * worker threads, deblocks (optional) and converts to RGBA.  Returns wall seconds (<0 on
+ * error); adds the luma pixels produced to *pixels and the RGBA checksums to *checksum. */
+typedef struct orc_batch orc_batch;
+orc_batch* orc_batch_new(int n_streams, int decoder_options);
+void orc_batch_free(orc_batch*);
+double orc_batch_step(orc_batch*, const uint8_t* blob, const uint64_t* pkt_off, const uint32_t* pkt_len,
+                      int do_deblock, int threads, uint64_t* pixels, uint64_t* checksum);
+/* planes / RGBA of stream s after the last step (for cross-checks) */
+int orc_batch_stream_yuv(orc_batch*, int s, uint8_t* y, uint8_t* cb, uint8_t* cr);
+
 #ifdef __cplusplus
 }
 #endif

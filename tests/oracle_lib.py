@@ -76,6 +76,13 @@ def lib():
     L.orc_bench_decode.restype = C.c_double
     L.orc_bench_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.orc_batch_new.restype = C.c_void_p
+    L.orc_batch_new.argtypes = [C.c_int, C.c_int]
+    L.orc_batch_free.argtypes = [C.c_void_p]
+    L.orc_batch_step.restype = C.c_double
+    L.orc_batch_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.orc_batch_stream_yuv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -1,0 +1,211 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle -- bit exact
+Y/Cb/Cr planes and bit exact RGBA on the same seeded bitstreams, plus the reference's own
+known-answer vectors for the colour conversion and the deblocking filter."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import oracle_decode_stream, weighted_sum
+from h263_rs_b200 import _lib, api, frontend, synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    with open(os.path.join(G, name)) as f:
+        return json.load(f)
+
+
+# ------------------------------------------------------------------ yuv::bt601 (K4)
+def test_yuv420_to_rgba_reference_kats():
+    k = load("kat_yuv.json")
+    for v in k["yuv_to_rgb"]:
+        y, cb, cr = v["yuv"]
+        assert list(api.yuv420_to_rgba([y], [cb], [cr], 1)) == v["rgb"] + [255]
+    for p in k["yuv420_to_rgba"]:
+        assert list(api.yuv420_to_rgba(p["y"], p["cb"], p["cr"], p["width"])) == p["rgba"], p["width"]
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 2), (3, 5), (5, 4), (7, 3), (16, 16), (33, 17), (176, 144), (352, 288), (355, 291)])
+def test_yuv420_to_rgba_random_planes(w, h):
+    rng = np.random.default_rng(w * 1000 + h)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    y = rng.integers(0, 256, w * h).astype(np.uint8)
+    cb = rng.integers(0, 256, cw * ch).astype(np.uint8)
+    cr = rng.integers(0, 256, cw * ch).astype(np.uint8)
+    assert np.array_equal(api.yuv420_to_rgba(y, cb, cr, w), O.yuv420_to_rgba(y, cb, cr, w))
+
+
+# ------------------------------------------------------------------ deblock (K3)
+def test_deblock_reference_kats():
+    p = load("kat_deblock.json")["picture"]
+    for c in p["cases"]:
+        assert list(api.deblock(p["data"], p["width"], c["strength"])) == c["expected"], c["strength"]
+    assert list(api.QUANT_TO_STRENGTH) == load("kat_constants.json")["quant_to_strength"]
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (9, 17), (10, 10), (11, 17), (16, 16), (17, 9), (31, 33), (40, 24), (88, 72),
+                                 (176, 144), (352, 288), (357, 293)])
+def test_deblock_random_planes_including_scalar_tails(w, h):
+    rng = np.random.default_rng(w * 977 + h)
+    smooth = rng.integers(0, 256, (h // 8 + 1, w // 8 + 1)).astype(np.int32)
+    base = np.kron(smooth, np.ones((8, 8), np.int32))[:h, :w]
+    for amp in (3, 40):
+        data = np.clip(base + rng.integers(-amp, amp + 1, (h, w)), 0, 255).astype(np.uint8).reshape(-1)
+        for strength in (1, 4, 9, 12):
+            assert np.array_equal(api.deblock(data, w, strength), O.deblock(data, w, strength)), (amp, strength)
+
+
+# ------------------------------------------------------------------ fused recon (K1+K2+K4)
+STREAMS = [
+    # BASELINE.json config 1: single QCIF stream, 1 I + 29 P, decoded to RGBA
+    dict(id="config1_qcif", w=176, h=144, n=30, seed=1),
+    dict(id="cif_halfpel", w=352, h=288, n=8, seed=2, mv_mode=1),
+    dict(id="cif_borders_escapes", w=352, h=288, n=6, seed=3, mv_mode=2, pct_escape=20, permille_overflow=30,
+         truncate_permille=300),
+    dict(id="cif_v0_escapes", w=352, h=288, n=4, seed=4, version=0, pct_escape=30),
+    dict(id="qcif_baseline_h263", w=176, h=144, n=6, seed=5, flavour=1, pct_escape=10),
+    dict(id="160x120_4mv_dquant", w=160, h=120, n=8, seed=6, pct_fourmv=30, pct_dquant=40, mv_mode=1),
+    dict(id="200x100_unaligned", w=200, h=100, n=6, seed=7, intra_period=3, mv_mode=2),
+    dict(id="4cif", w=704, h=576, n=3, seed=8, mv_mode=2),
+    dict(id="sqcif_many_events", w=128, h=96, n=4, seed=9, mean_events_x10=200, pct_cbp_inter=90),
+    dict(id="tiny_24x40", w=24, h=40, n=5, seed=10, mv_mode=1),
+    dict(id="qcif_all_intra_dense", w=176, h=144, n=3, seed=11, intra_period=1, pct_cbp_intra=100, mean_events_x10=120),
+]
+
+
+def _packets(c):
+    kw = {k: v for k, v in c.items() if k not in ("id", "w", "h", "n", "seed")}
+    return synth.make_stream(c["w"], c["h"], c["n"], c["seed"], **kw), (0 if kw.get("flavour", 0) == 1 else 1)
+
+
+@pytest.mark.parametrize("case", STREAMS, ids=lambda c: c["id"])
+def test_decode_next_picture_bit_exact(case):
+    packets, opt = _packets(case)
+    ref = oracle_decode_stream(packets, opt)
+    st = api.H263State(opt)
+    for i, pk in enumerate(packets):
+        if isinstance(ref[i], int):
+            with pytest.raises(_lib.H263Error):
+                st.decode_next_picture(pk)
+            continue
+        st.decode_next_picture(pk)
+        pic = st.get_last_picture()
+        y, cb, cr = pic.as_yuv()
+        assert (pic.width, pic.height) == (ref[i]["info"]["width"], ref[i]["info"]["height"])
+        assert np.array_equal(y, ref[i]["y"]), (case["id"], i, "Y")
+        assert np.array_equal(cb, ref[i]["cb"]), (case["id"], i, "Cb")
+        assert np.array_equal(cr, ref[i]["cr"]), (case["id"], i, "Cr")
+        assert np.array_equal(st.get_last_rgba(), ref[i]["rgba"]), (case["id"], i, "RGBA")
+
+
+@pytest.mark.parametrize("case", [STREAMS[0], STREAMS[2], STREAMS[6], STREAMS[7]], ids=lambda c: c["id"])
+def test_deblocked_rgba_bit_exact(case):
+    """recon -> deblock(plane, width, QUANT_TO_STRENGTH[pquant]) per plane -> RGBA; the
+    reference frames stay un-deblocked (BASELINE.json config 4 composition)."""
+    packets, opt = _packets(dict(case, deblock_flag=1))
+    ref = oracle_decode_stream(packets, opt, deblock=True)
+    st = api.H263State(opt, deblock=True)
+    for i, pk in enumerate(packets):
+        if isinstance(ref[i], int):
+            with pytest.raises(_lib.H263Error):
+                st.decode_next_picture(pk)
+            continue
+        st.decode_next_picture(pk)
+        y, cb, cr = st.get_last_picture().as_yuv()
+        assert np.array_equal(y, ref[i]["y"]) and np.array_equal(cb, ref[i]["cb"]) and np.array_equal(cr, ref[i]["cr"])
+        assert np.array_equal(st.get_last_rgba(), ref[i]["rgba"]), (case["id"], i)
+
+
+def test_batch_decoder_many_streams_and_device_checksums():
+    """16 independent CIF streams decoded in lock step; per-stream planes, RGBA and the
+    on-device checksums all match the oracle (the form configs 3-5 use at full size)."""
+    n, t_steps = 16, 5
+    streams = [synth.make_stream(352, 288, t_steps, 1000 + s, mv_mode=s % 3, pct_fourmv=5 + s) for s in range(n)]
+    refs = [oracle_decode_stream(p) for p in streams]
+    dec = api.BatchDecoder(n, 352, 288, threads=4)
+    for t in range(t_steps):
+        errs = dec.decode_step([streams[s][t] for s in range(n)])
+        assert not errs.any()
+        dec.ctx.sync()
+        sums = dec.ctx.checksums(np.arange(n))
+        for s in range(n):
+            r = refs[s][t]
+            assert [int(v) for v in sums[s]] == [weighted_sum(r["y"]), weighted_sum(r["cb"]), weighted_sum(r["cr"]),
+                                                 weighted_sum(r["rgba"])], (s, t)
+        for s in (0, 7, 15):
+            y, cb, cr = dec.ctx.read_yuv(s)
+            assert np.array_equal(y, refs[s][t]["y"]) and np.array_equal(cb, refs[s][t]["cb"])
+            assert np.array_equal(cr, refs[s][t]["cr"])
+            assert np.array_equal(dec.ctx.read_rgba(s), refs[s][t]["rgba"])
+
+
+def test_resident_steps_replay_and_mixed_sizes():
+    """Side info resident in device memory (step_upload/step_run), streams of different
+    picture sizes in one step, and a stream that sits out a step."""
+    dims = [(176, 144), (352, 288), (160, 120), (128, 96)]
+    t_steps = 4
+    streams = [synth.make_stream(w, h, t_steps, 50 + i, mv_mode=1) for i, (w, h) in enumerate(dims)]
+    refs = [oracle_decode_stream(p) for p in streams]
+    ctx = api.Context(0, len(dims), 352, 288)
+    parsers = [frontend.Parser(1) for _ in dims]
+    decoded = [0] * len(dims)
+    for t in range(t_steps + 1):
+        active = [s for s in range(len(dims)) if not (s == 2 and t == 1) and decoded[s] < t_steps]
+        if not active:
+            break
+        pics, mbs, events, errs, _ = frontend.parse_step([parsers[s] for s in active],
+                                                         [streams[s][decoded[s]] for s in active], active, 2)
+        assert not errs.any()
+        step = ctx.step_upload(pics, mbs, events)
+        ctx.step_run(step, _lib.OUT_RGBA)
+        ctx.sync()
+        ctx.step_free(step)
+        for s in active:
+            r = refs[s][decoded[s]]
+            y, cb, cr = ctx.read_yuv(s)
+            assert np.array_equal(y, r["y"]) and np.array_equal(cb, r["cb"]) and np.array_equal(cr, r["cr"]), (s, t)
+            assert np.array_equal(ctx.read_rgba(s), r["rgba"]), (s, t)
+            decoded[s] += 1
+
+
+def test_readback_pipeline_matches():
+    """submit_step_readback: RGBA of every step copied back asynchronously (the e2e path)."""
+    import ctypes as C
+
+    n, t_steps = 6, 4
+    streams = [synth.make_stream(176, 144, t_steps, 300 + s) for s in range(n)]
+    refs = [oracle_decode_stream(p) for p in streams]
+    dec = api.BatchDecoder(n, 176, 144, threads=2)
+    L = _lib.lib()
+    size = 176 * 144 * 4
+    bufs = []
+    for t in range(t_steps):
+        pics, mbs, events, errs, _ = dec.parse_step([streams[s][t] for s in range(n)])
+        host = L.h263cu_alloc_pinned(n * size)
+        assert host
+        bufs.append(host)
+        _lib.check(L.h263cu_submit_step_readback(dec.ctx.h, pics.ctypes.data, len(pics), mbs.ctypes.data, len(mbs),
+                                                 events.ctypes.data, len(events), _lib.OUT_RGBA, host, None))
+    dec.ctx.sync()
+    for t in range(t_steps):
+        arr = np.ctypeslib.as_array(C.cast(bufs[t], C.POINTER(C.c_uint8)), shape=(n * size,))
+        for s in range(n):
+            assert np.array_equal(arr[s * size : (s + 1) * size], refs[s][t]["rgba"]), (s, t)
+        L.h263cu_free_pinned(bufs[t])
+
+
+def test_device_errors_are_loud():
+    ctx = api.Context(0, 2, 176, 144)
+    pk = synth.make_stream(352, 288, 1, 1)
+    pic, mbs, ev = frontend.Parser(1).parse_picture(pk[0])
+    with pytest.raises(_lib.H263Error) as e:  # picture larger than the context
+        ctx.submit_step(pic, mbs, ev, _lib.OUT_RGBA)
+    assert e.value.code == _lib.ERR_CAPACITY
+    with pytest.raises(_lib.H263Error) as e:
+        ctx.read_yuv(0)
+    assert e.value.code == _lib.ERR_NO_PICTURE
