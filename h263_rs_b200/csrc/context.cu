@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -48,6 +49,7 @@ struct StreamState {
     uint8_t pic_type = 0, pquant = 0;
     uint16_t tr = 0;
     uint32_t stamp = 0;
+    bool padded = false;  // the last picture's planes carry the replicated border (tiled kernel)
 };
 
 }  // namespace
@@ -102,10 +104,12 @@ struct h263cu_ctx {
     unsigned long long* d_sums = nullptr;
     size_t jobs_cap = 0;
 
+    int force_kernel = 0;  // H263CU_KERNEL=mb|tile overrides the per-step choice (A/B checks)
+    // interior origin (pixel 0,0) of a plane; the padding lies at negative offsets
     uint8_t* plane(int p, uint32_t stream, int slot) const {
         const size_t idx = (size_t)stream * 2 + (size_t)slot;
-        if (p == 0) return y_pool + idx * y_slot;
-        return (p == 1 ? cb_pool : cr_pool) + idx * c_slot;
+        if (p == 0) return y_pool + idx * y_slot + (size_t)PAD_Y_ROWS * pitch_y + PAD_Y_COLS;
+        return (p == 1 ? cb_pool : cr_pool) + idx * c_slot + (size_t)PAD_C_ROWS * pitch_c + PAD_C_COLS;
     }
     uint8_t* rgba(uint32_t stream, int slot) const { return rgba_pool + ((size_t)slot * max_streams + stream) * rgba_slot; }
 };
@@ -173,6 +177,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     const bool want_deblock = want_rgba && (out_flags & H263CU_OUT_DEBLOCK) != 0;
     c->stamp++;
     uint32_t max_w = 0, max_h = 0;
+    bool tiled = true;
     for (uint32_t i = 0; i < n; i++) {
         const h263cu_pic& p = s->pics[i];
         if (p.stream >= c->max_streams) return H263CU_ERR_CAPACITY;
@@ -192,7 +197,11 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         }
         max_w = std::max<uint32_t>(max_w, p.width);
         max_h = std::max<uint32_t>(max_h, p.height);
+        // the tiled kernel needs MB-aligned pictures and references with a replicated border
+        if ((p.width | p.height) & 15) tiled = false;
+        if ((p.flags & H263CU_PICFLAG_HAS_INTER) && !st.padded) tiled = false;
     }
+    if (c->force_kernel == 1) tiled = false;
     int e = ensure_pic_ring(c, n);
     if (e) return e;
     const int slot = c->pic_ring_pos;
@@ -225,6 +234,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         st.w = p.width, st.h = p.height;
         st.pic_type = p.pic_type, st.pquant = p.pquant, st.tr = p.temporal_reference;
         st.rgba_slot = want_rgba ? (int8_t)rgba_ring : (int8_t)-1;
+        st.padded = tiled;
     }
     CU_TRY(cudaMemcpyAsync(c->d_pics[slot], hp, n * sizeof(PicDev), cudaMemcpyHostToDevice, c->s_main));
     CU_TRY(cudaEventRecord(c->pics_done[slot], c->s_main));
@@ -234,7 +244,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     }
     cudaEvent_t pa = nullptr, pb = nullptr;
     if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
-    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, c->s_main);
+    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? 1 : 0, c->s_main);
     c->launches++;
     if (c->profiling) prof_end(c, pa, pb, 0);
     if (want_deblock) {
@@ -319,11 +329,14 @@ h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, 
     c->mbw = (max_width + 15) / 16, c->mbh = (max_height + 15) / 16;
     // planes are MB-rounded so that whole-macroblock stores never need predication; the
     // padding is never read as picture content (sample coordinates clamp to the true size)
-    c->pitch_y = c->mbw * 16;
-    c->pitch_c = (uint32_t)round_up(c->mbw * 8, 16);
+    // plus a border (PAD_*) into which the tiled kernel replicates the edge pixels, so that
+    // motion compensation needs no per-sample clamping (unrestricted-MV extension)
+    c->pitch_y = c->mbw * 16 + 2 * PAD_Y_COLS;
+    c->pitch_c = (uint32_t)round_up(c->mbw * 8 + 2 * PAD_C_COLS, 16);
     c->rgba_pitch = c->mbw * 16 * 4;
-    c->y_slot = (size_t)c->pitch_y * c->mbh * 16;
-    c->c_slot = (size_t)c->pitch_c * c->mbh * 8;
+    c->y_slot = (size_t)c->pitch_y * (c->mbh * 16 + 2 * PAD_Y_ROWS);
+    c->c_slot = (size_t)c->pitch_c * (c->mbh * 8 + 2 * PAD_C_ROWS);
+    if (const char* k = getenv("H263CU_KERNEL")) c->force_kernel = !strcmp(k, "mb") ? 1 : (!strcmp(k, "tile") ? 2 : 0);
     c->rgba_slot = (size_t)c->rgba_pitch * c->mbh * 16;
     c->streams.resize(max_streams);
     auto fail = [&](int code) {

@@ -26,8 +26,15 @@ struct PicDev {
 
 // Fused reconstruction of every macroblock of a step: inverse RLE + dequant + classify +
 // IDCT + motion compensation + add/clamp -> planes, and BT.601 RGBA when `emit_rgba`.
+// tiled != 0 selects recon_tile_kernel (picture sizes multiple of 16, padded reference planes),
+// else the generic warp-per-macroblock recon_mb_kernel.
 void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
-                  int emit_rgba, cudaStream_t stream);
+                  int emit_rgba, int tiled, cudaStream_t stream);
+
+// Plane padding (bytes / rows) reserved around every reconstruction plane: the tiled kernel
+// replicates 16 luma / 8 chroma border pixels into it; the extra columns keep the interior
+// origin 32 B / 16 B aligned and absorb aligned-word over-reads.
+constexpr int PAD_Y_COLS = 32, PAD_Y_ROWS = 16, PAD_C_COLS = 16, PAD_C_ROWS = 8;
 
 // Deblocking post-filter (per plane, per picture) fused with the RGBA conversion.
 // grid = (max tiles per picture, n_pics).
