@@ -220,6 +220,11 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
             d.ref[k] = st.has_pic ? c->plane(k, p.stream, ref_slot) : nullptr;
         }
         d.rgba = want_rgba ? c->rgba(p.stream, rgba_ring) : nullptr;
+        d.cur_y4 = (uint32_t)((d.cur[0] - c->y_pool) >> 2);
+        d.cur_c4 = (uint32_t)((d.cur[1] - c->cb_pool) >> 2);
+        d.ref_y4 = st.has_pic ? (uint32_t)((d.ref[0] - c->y_pool) >> 2) : 0u;
+        d.ref_c4 = st.has_pic ? (uint32_t)((d.ref[1] - c->cb_pool) >> 2) : 0u;
+        d.rgba16 = want_rgba ? (uint32_t)((d.rgba - c->rgba_pool) >> 4) : 0u;
         d.first_event = p.first_event;
         d.rgba_pitch = c->rgba_pitch;
         d.w = p.width, d.h = p.height;
@@ -244,7 +249,8 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     }
     cudaEvent_t pa = nullptr, pb = nullptr;
     if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
-    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? 1 : 0, c->s_main);
+    const Pools pools{c->y_pool, c->cb_pool, c->cr_pool, c->rgba_pool};
+    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? 1 : 0, pools, c->s_main);
     c->launches++;
     if (c->profiling) prof_end(c, pa, pb, 0);
     if (want_deblock) {
@@ -345,6 +351,9 @@ h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, 
         return (h263cu_ctx*)nullptr;
     };
     const size_t pad = 256;  // aligned-word prediction loads may run a few bytes past a row
+    // the tiled kernel addresses the pools through 32-bit offsets: 4-byte units for the planes,
+    // 16-byte units for RGBA
+    if (c->y_slot * 2 * max_streams + pad >= (16ull << 30) || c->rgba_slot * 2 * max_streams + pad >= (64ull << 30)) return fail(H263CU_ERR_CAPACITY);
     if (cudaMalloc((void**)&c->y_pool, c->y_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
     if (cudaMalloc((void**)&c->cb_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
     if (cudaMalloc((void**)&c->cr_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);

@@ -22,6 +22,20 @@ struct PicDev {
     uint8_t strength;       // QUANT_TO_STRENGTH[pquant]
     uint8_t flags;
     uint8_t pad[2];
+    // the same planes as 32-bit offsets from the context's pools (tiled kernel): interior origin
+    // of the Y plane in 4-byte units from y_pool, of the Cb / Cr planes in 4-byte units from
+    // cb_pool / cr_pool (both pools share one layout), RGBA picture in 16-byte units from rgba_pool
+    uint32_t cur_y4, cur_c4, ref_y4, ref_c4, rgba16;
+    uint32_t pad2;
+};
+
+// Pool base pointers of a context: kernel parameters of the tiled kernel (uniform registers),
+// so that per-macroblock state in shared memory can be 32-bit offsets instead of pointers.
+struct Pools {
+    uint8_t* y;
+    uint8_t* cb;
+    uint8_t* cr;
+    uint8_t* rgba;
 };
 
 // Fused reconstruction of every macroblock of a step: inverse RLE + dequant + classify +
@@ -29,7 +43,10 @@ struct PicDev {
 // tiled != 0 selects recon_tile_kernel (picture sizes multiple of 16, padded reference planes),
 // else the generic warp-per-macroblock recon_mb_kernel.
 void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
-                  int emit_rgba, int tiled, cudaStream_t stream);
+                  int emit_rgba, int tiled, const Pools& pools, cudaStream_t stream);
+// recon_tile.cu
+void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
+                       int emit_rgba, const Pools& pools, cudaStream_t stream);
 
 // Plane padding (bytes / rows) reserved around every reconstruction plane: the tiled kernel
 // replicates 16 luma / 8 chroma border pixels into it; the extra columns keep the interior
