@@ -21,10 +21,10 @@ DEPS = SOURCES + ["kernels.cuh", "recon_common.cuh", "device_math.cuh", "bitio.h
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
-def nvcc_cmd(extra=()):
+def nvcc_cmd(extra=(), out=None):
     return [
         NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-        "-Xcompiler", "-fPIC,-O2,-pthread,-ffp-contract=off", "-shared", "-o", OUT,
+        "-Xcompiler", "-fPIC,-O2,-pthread,-ffp-contract=off", "-shared", "-o", out or OUT,
         *[os.path.join(CSRC, s) for s in SOURCES], *extra,
     ]
 
@@ -46,6 +46,17 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
     return OUT
+
+
+def build_variant(name, defines):
+    """Side-by-side experiment builds: libh263cu_<name>.so with extra -D flags; select one at run
+    time with H263CU_LIB=<path> (see _lib.py).  Not part of the product build."""
+    out = os.path.join(HERE, "libh263cu_%s.so" % name)
+    r = subprocess.run(nvcc_cmd(["-D" + d for d in defines], out), capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed for variant " + name)
+    return out
 
 
 if __name__ == "__main__":

@@ -100,6 +100,7 @@ struct h263cu_ctx {
     };
     std::vector<ProfSpan> prof_spans;
     // checksum scratch
+    uint32_t* d_work_counter = nullptr;  // tile counter of the persistent recon kernel
     ChecksumJob* d_jobs = nullptr;
     unsigned long long* d_sums = nullptr;
     size_t jobs_cap = 0;
@@ -249,7 +250,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     }
     cudaEvent_t pa = nullptr, pb = nullptr;
     if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
-    const Pools pools{c->y_pool, c->cb_pool, c->cr_pool, c->rgba_pool};
+    const Pools pools{c->y_pool, c->cb_pool, c->cr_pool, c->rgba_pool, c->d_work_counter};
     launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? 1 : 0, pools, c->s_main);
     c->launches++;
     if (c->profiling) prof_end(c, pa, pb, 0);
@@ -358,6 +359,7 @@ h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, 
     if (cudaMalloc((void**)&c->cb_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
     if (cudaMalloc((void**)&c->cr_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
     if (cudaMalloc((void**)&c->rgba_pool, c->rgba_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc((void**)&c->d_work_counter, 256) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
     if (cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
@@ -407,6 +409,7 @@ void h263cu_destroy(h263cu_ctx* c) {
     for (auto e : c->prof_free) cudaEventDestroy(e);
     if (c->d_jobs) cudaFree(c->d_jobs);
     if (c->d_sums) cudaFree(c->d_sums);
+    if (c->d_work_counter) cudaFree(c->d_work_counter);
     if (c->y_pool) cudaFree(c->y_pool);
     if (c->cb_pool) cudaFree(c->cb_pool);
     if (c->cr_pool) cudaFree(c->cr_pool);

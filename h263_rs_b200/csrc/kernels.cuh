@@ -36,6 +36,7 @@ struct Pools {
     uint8_t* cb;
     uint8_t* cr;
     uint8_t* rgba;
+    uint32_t* work_counter;  // next tile index of the persistent tiled kernel (reset before every launch)
 };
 
 // Fused reconstruction of every macroblock of a step: inverse RLE + dequant + classify +
