@@ -250,7 +250,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     }
     cudaEvent_t pa = nullptr, pb = nullptr;
     if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
-    const Pools pools{c->y_pool, c->cb_pool, c->cr_pool, c->rgba_pool, c->d_work_counter};
+    const Pools pools{c->y_pool, c->cb_pool, c->cr_pool, c->rgba_pool, c->d_work_counter, c->pitch_y, c->pitch_c, c->rgba_pitch};
     launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? 1 : 0, pools, c->s_main);
     c->launches++;
     if (c->profiling) prof_end(c, pa, pb, 0);

@@ -37,6 +37,7 @@ struct Pools {
     uint8_t* cr;
     uint8_t* rgba;
     uint32_t* work_counter;  // next tile index of the persistent tiled kernel (reset before every launch)
+    uint32_t pitch_y, pitch_c, rgba_pitch;  // row pitches shared by every plane of the context (bytes)
 };
 
 // Fused reconstruction of every macroblock of a step: inverse RLE + dequant + classify +

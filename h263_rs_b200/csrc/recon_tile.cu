@@ -32,14 +32,30 @@ constexpr int WARP_MBS = 4;      // macroblocks per warp
 #ifndef H263_PERSISTENT
 #define H263_PERSISTENT 0
 #endif
+#ifndef H263_PREFETCH_L2
+#define H263_PREFETCH_L2 0
+#endif
+#ifndef H263_LDG64
+#define H263_LDG64 0
+#endif
+#ifndef H263_MIN_CTAS
+#define H263_MIN_CTAS (32 / H263_CTA_WARPS)
+#endif
 constexpr int CTA_WARPS = H263_CTA_WARPS;
 // Persistent warps drawing tiles from a global counter were measured SLOWER than one CTA per 32
 // consecutive macroblocks (325 vs 303 us per 1024-CIF step): neighbouring tiles then run on different
 // SMs and lose the L1 sharing of overlapping prediction windows (L1 hit rate 48 % vs 58 %), and partial
 // DRAM write atoms of chroma rows are no longer merged.  Kept as a build option for the record.
 constexpr bool kPersistent = H263_PERSISTENT != 0;
+// Tiles per warp (non-persistent build): warp w of CTA b takes tiles (b*T + it)*CTA_WARPS + w, it < T,
+// so the CTA's warps stay on neighbouring macroblocks while the per-warp work averages out.
+#ifndef H263_TILES_PER_WARP
+#define H263_TILES_PER_WARP 1
+#endif
+constexpr int kTilesPerWarp = H263_TILES_PER_WARP;
 constexpr int CTA_THREADS = CTA_WARPS * 32;
 constexpr int WARP_BLOCKS = WARP_MBS * 6;
+constexpr int RES_WORDS = 36;
 constexpr int SLOT_FLOATS = 68;  // 64 + 4 pad: 16 B aligned, the four slots of a pass start 4 banks apart
 
 // per-macroblock flags (WarpSmem.mb[][3])
@@ -51,7 +67,8 @@ constexpr uint32_t BF_SLOW = 1u << 4;  // the vector leaves the replicated borde
 
 struct __align__(16) WarpSmem {
     float coef[4][SLOT_FLOATS];        // coefficients of the four slots in flight -> row-pass output
-    uint32_t res[WARP_BLOCKS][32];     // per slot: 8 residual rows of 16 bytes, lanes (r0,r2)(r1,r3)(r4,r6)(r5,r7)
+    uint32_t res[WARP_BLOCKS][RES_WORDS];  // per slot: 8 residual rows of 16 bytes, lanes (r0,r2)(r1,r3)(r4,r6)(r5,r7);
+                                       // 4 words of padding put the four slots of a pass on different banks
     uint32_t mb[WARP_MBS][8];          // ydst, cdst, rgba, flags, pitches, rgba_pitch, pic, -
     uint2 slotdesc[WARP_BLOCKS];       // x = first event unit (absolute), y = nev | quant<<8 | wide<<13 | inter<<14 | block<<16 | dc<<24
     uint32_t mbrec[WARP_BLOCKS];       // the four macroblock records
@@ -86,6 +103,19 @@ __device__ __forceinline__ int dequant_narrow(int level, int q2, int qc) {
 // (v * B00) / 4 == (v / 4) * B00 exactly (power-of-two scaling) -- idct.rs:143-145,161-163,189-190
 __device__ __forceinline__ int round_q(float q, float m) { return __float2int_rz(fadd(fmul(q, m), copysign_half(q))); }
 // ---- half-pel interpolation in 16-bit lanes -------------------------------------------------
+// The three aligned words that hold the 9 bytes a prediction row needs, p = word of the first pixel.
+// With H263_LDG64 they come from two 8-byte loads of the enclosing 16-byte window (two requests
+// instead of three on the L1 data pipe, the busiest unit of this kernel); odd = p is an odd word.
+__device__ __forceinline__ void load_row3(const uint32_t* p, bool odd, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+#if H263_LDG64
+    const uint2* q = reinterpret_cast<const uint2*>(p - (odd ? 1 : 0));
+    const uint2 v0 = __ldg(q), v1 = __ldg(q + 1);
+    w0 = odd ? v0.y : v0.x, w1 = odd ? v1.x : v0.y, w2 = odd ? v1.y : v1.x;
+#else
+    w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+#endif
+}
+
 // One row of 8 pixels: a = bytes [s, s+8), b = bytes [s+ix, s+ix+8) of the 12 loaded bytes.
 // Returns a + b per pixel as four words of two 16-bit lanes: e0 = (p0, p2), o0 = (p1, p3),
 // e1 = (p4, p6), o1 = (p5, p7).  With ix = 0 this is 2a.
@@ -144,7 +174,11 @@ __device__ __forceinline__ uint32_t splat_hi(uint32_t w) { return __byte_perm(w,
 }  // namespace
 
 
-__global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
+// PY / PC / PR: luma, chroma and RGBA row pitches in bytes when they are known at compile time (the
+// standard picture formats; all planes of a context share them), 0 = read them from the descriptors.
+// Constant pitches turn every row address of the epilogue into an immediate offset.
+template <int PY, int PC, int PR>
+__global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
     recon_tile_kernel(const PicDev* __restrict__ pics, const h263cu_mb* __restrict__ mbs,
                       const h263cu_event* __restrict__ events, uint32_t n_mbs, int emit_rgba, const Pools pools) {
     __shared__ __align__(16) TileSmem S;
@@ -163,7 +197,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
     // while a neighbour works on a heavier tile.  The next tile number is drawn at the top of a tile and
     // its record words are fetched before the epilogue, one tile ahead of their use.
     const uint32_t n_tiles = (n_mbs + WARP_MBS - 1) / WARP_MBS;
-    uint32_t tile = blockIdx.x * CTA_WARPS + warp;
+    uint32_t tile = (kPersistent ? blockIdx.x : blockIdx.x * kTilesPerWarp) * CTA_WARPS + warp;
+    int tiles_left = kTilesPerWarp;
     const uint32_t* mbs32 = reinterpret_cast<const uint32_t*>(mbs);
     uint32_t rec = 0;
     if (tile < n_tiles && (uint32_t)lane < min((uint32_t)WARP_MBS, n_mbs - tile * WARP_MBS) * 6) rec = __ldg(mbs32 + (size_t)tile * WARP_BLOCKS + lane);
@@ -171,7 +206,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
     const uint32_t mb0 = tile * WARP_MBS;
     const int n_w = (int)min((uint32_t)WARP_MBS, n_mbs - mb0);
     uint32_t next_tile = 0;
-    if (!kPersistent) next_tile = n_tiles;
+    if (!kPersistent) next_tile = --tiles_left > 0 ? tile + CTA_WARPS : n_tiles;
     else if (lane == 0) next_tile = gridDim.x * CTA_WARPS + atomicAdd(pools.work_counter, 1u);
 
     // ================= phase 0: lane = block (macroblock lane / 6, block lane % 6) ==============
@@ -202,7 +237,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
                 mvx = (int8_t)(mvw & 0xFF), mvy = (int8_t)((mvw >> 8) & 0xFF);
                 in_range = mvx >= -32 && mvx <= 31 && mvy >= -32 && mvy <= 31;
                 sx = mbx * 16 + (bb & 1) * 8 + (mvx >> 1), sy = mby * 16 + (bb >> 1) * 8 + (mvy >> 1);
-                pitch = P.pitch_y, base = P.ref_y4;
+                pitch = PY ? PY : P.pitch_y, base = P.ref_y4;
             } else {
                 // both chroma blocks use the average of the four luma vectors (gather.rs:182, types.rs:759-768)
                 const int sumx = (int8_t)byte_of(w4, 0) + (int8_t)byte_of(w4, 2) + (int8_t)byte_of(w5, 0) + (int8_t)byte_of(w5, 2);
@@ -210,19 +245,28 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
                 mvx = average_sum_of_mvs(sumx), mvy = average_sum_of_mvs(sumy);
                 in_range = mvx >= -16 && mvx <= 15 && mvy >= -16 && mvy <= 15;
                 sx = mbx * 8 + (mvx >> 1), sy = mby * 8 + (mvy >> 1);
-                pitch = P.pitch_c, base = P.ref_c4;
+                pitch = PC ? PC : P.pitch_c, base = P.ref_c4;
             }
             const int a = sx & 3;
             boff = base + (uint32_t)((sy * pitch + (sx - a)) >> 2);
             bflags = (uint32_t)(a | ((mvx & 1) << 2) | ((mvy & 1) << 3)) | (in_range ? 0u : BF_SLOW);
+#if H263_PREFETCH_L2
+            // the 9 source rows of this block (reference planes are DRAM-resident: written a step ago):
+            // start the DRAM -> L2 transfer now, the epilogue loads them ~1000 instructions later
+            if (bvalid && in_range) {
+                const uint8_t* pbase = (bb < 4 ? pools.y : (bb == 4 ? pools.cb : pools.cr)) + (size_t)boff * 4;
+#pragma unroll
+                for (int rr = 0; rr < 9; rr++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pbase + (size_t)rr * pitch));
+            }
+#endif
         }
         if (bvalid) {
             W.bd[lane] = boff;
             W.bf[lane] = bflags;
             if (bb == 0) {
-                const int pitch_y = P.pitch_y, pitch_c = P.pitch_c;
+                const int pitch_y = PY ? PY : P.pitch_y, pitch_c = PC ? PC : P.pitch_c;
                 const int mbw = P.w >> 4, mbh = P.h >> 4;
-                const uint32_t rgba_pitch = P.rgba_pitch;
+                const uint32_t rgba_pitch = PR ? PR : P.rgba_pitch;
                 uint32_t flags = inter ? MBF_INTER : 0u;
                 if (mbx == 0) flags |= MBF_LEFT;
                 if (mbx == mbw - 1) flags |= MBF_RIGHT;
@@ -376,15 +420,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
                 }
                 if (R) {
                     // pixel (x = t, y = j): residual row j of the slot, 16-bit lane of column t in the lane
-                    // order of phase 3, (r0,r2) (r1,r3) (r4,r6) (r5,r7); rows are XOR-swizzled by the slot
-                    // number so that the four slots of a pass hit different banks
+                    // order of phase 3, (r0,r2) (r1,r3) (r4,r6) (r5,r7)
                     const float m = vert ? H263_B00 : 1.0f;
                     uint16_t* rrow = reinterpret_cast<uint16_t*>(&W.res[si][0]) + ((t & 1) + 2 * (t >> 2)) * 2 + ((t >> 1) & 1);
-                    const int sw = si & 7;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const int r = round_q(acc[j], m);
-                        rrow[(j ^ sw) * 8] = (uint16_t)(int16_t)max(min(r, 255), -256);
+                        rrow[j * 8] = (uint16_t)(int16_t)max(min(r, 255), -256);
                     }
                 }
             }
@@ -394,7 +436,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
 
     // the next tile's record words: in flight during the epilogue
     if (kPersistent) next_tile = __shfl_sync(FULL, next_tile, 0);
-    if (kPersistent && next_tile < n_tiles && (uint32_t)lane < min((uint32_t)WARP_MBS, n_mbs - next_tile * WARP_MBS) * 6)
+    if ((kPersistent || kTilesPerWarp > 1) && next_tile < n_tiles && (uint32_t)lane < min((uint32_t)WARP_MBS, n_mbs - next_tile * WARP_MBS) * 6)
         rec = __ldg(mbs32 + (size_t)next_tile * WARP_BLOCKS + lane);
 
     // ================= phase 3: MC + add + clamp + stores + RGBA, all in registers ===============
@@ -408,7 +450,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
         const uint4 ma = *reinterpret_cast<const uint4*>(&W.mb[mbi][0]);
         const uint4 mv = *reinterpret_cast<const uint4*>(&W.mb[mbi][4]);
         const uint32_t flags = unit_ok ? ma.w : 0u;
-        const uint32_t pitch_y4 = (mv.x & 0xFFFFu) >> 2, pitch_c4 = mv.x >> 18;
+        const uint32_t pitch_y4 = PY ? PY / 4 : (mv.x & 0xFFFFu) >> 2, pitch_c4 = PC ? PC / 4 : mv.x >> 18;
         const int lb = ((rg >> 1) << 1) | h;  // luma block of this unit
         const int r0 = (rg & 1) * 4;          // first row of the unit inside its block
         const int bl = mbi * 6 + lb, bc = mbi * 6 + 4 + h;
@@ -420,14 +462,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
             if (!(fl & BF_SLOW)) {
                 const int sh = (fl & 3u) * 8, shb = sh + ((fl & 4u) << 1);
                 const uint32_t wb = (fl >> 3) & 1u, wt = 2u - wb;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(pools.y) + W.bd[bl] + (uint32_t)r0 * pitch_y4;
+                const uint32_t so = W.bd[bl];
+                const bool odd = (so & 1u) != 0;  // row pitches are multiples of 16 bytes: the same for every row
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(pools.y) + so + (uint32_t)r0 * pitch_y4;
                 RowSum hs[5];
 #pragma unroll
                 for (int r = 0; r < 5; r++) {
                     // the fifth row is only needed for vertical interpolation; without it the load
                     // repeats row 3 (an L1 hit) and its weight is 0
                     const uint32_t* p = src + (r < 4 ? (uint32_t)r : 3u + wb) * pitch_y4;
-                    hs[r] = row_sum8(__ldg(p), __ldg(p + 1), __ldg(p + 2), sh, shb);
+                    uint32_t w0, w1, w2;
+                    load_row3(p, odd, w0, w1, w2);
+                    hs[r] = row_sum8(w0, w1, w2, sh, shb);
                 }
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
@@ -455,12 +501,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
                 const int sh = (fc & 3u) * 8, shb = sh + ((fc & 4u) << 1);
                 const uint32_t wb = (fc >> 3) & 1u, wt = 2u - wb;
                 // chroma rows 2*rg, 2*rg+1 of the macroblock, all 8 columns, plane h
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(h ? pools.cr : pools.cb) + W.bd[bc] + (uint32_t)(rg * 2) * pitch_c4;
+                const uint32_t so = W.bd[bc];
+                const bool odd = (so & 1u) != 0;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(h ? pools.cr : pools.cb) + so + (uint32_t)(rg * 2) * pitch_c4;
                 RowSum hs[3];
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
                     const uint32_t* p = src + (r < 2 ? (uint32_t)r : 1u + wb) * pitch_c4;
-                    hs[r] = row_sum8(__ldg(p), __ldg(p + 1), __ldg(p + 2), sh, shb);
+                    uint32_t w0, w1, w2;
+                    load_row3(p, odd, w0, w1, w2);
+                    hs[r] = row_sum8(w0, w1, w2, sh, shb);
                 }
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
@@ -509,7 +559,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
                 const uint32_t* c = &W.res[rs][0];
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    const uint4 rv = *reinterpret_cast<const uint4*>(c + (((uint32_t)(r0 + r)) ^ (rs & 7u)) * 4);
+                    const uint4 rv = *reinterpret_cast<const uint4*>(c + (r0 + r) * 4);
                     ly[r].e0 = __viaddmin_s16x2_relu(ly[r].e0, rv.x, 0x00FF00FFu);
                     ly[r].o0 = __viaddmin_s16x2_relu(ly[r].o0, rv.y, 0x00FF00FFu);
                     ly[r].e1 = __viaddmin_s16x2_relu(ly[r].e1, rv.z, 0x00FF00FFu);
@@ -532,7 +582,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
                 const uint32_t* c = &W.res[rs][0];
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
-                    const uint4 rv = *reinterpret_cast<const uint4*>(c + (((uint32_t)(rg * 2 + r)) ^ (rs & 7u)) * 4);
+                    const uint4 rv = *reinterpret_cast<const uint4*>(c + (rg * 2 + r) * 4);
                     cy[r].e0 = __viaddmin_s16x2_relu(cy[r].e0, rv.x, 0x00FF00FFu);
                     cy[r].o0 = __viaddmin_s16x2_relu(cy[r].o0, rv.y, 0x00FF00FFu);
                     cy[r].e1 = __viaddmin_s16x2_relu(cy[r].e1, rv.z, 0x00FF00FFu);
@@ -630,7 +680,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 32 / CTA_WARPS)
                 ce[1][r] = h ? mine_e : got_e, co[1][r] = h ? mine_o : got_o;
             }
             if (flags & MBF_RGBA) {
-                const uint32_t rgba_pitch = mv.y;
+                const uint32_t rgba_pitch = PR ? PR : mv.y;
                 uint8_t* o = pools.rgba + (size_t)ma.z * 16 + (size_t)(rg * 4) * rgba_pitch + (size_t)(h * 32);
 #pragma unroll
                 for (int cr2 = 0; cr2 < 2; cr2++) {
@@ -665,17 +715,26 @@ void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_ev
                        const Pools& pools, cudaStream_t stream) {
     if (n_mbs == 0) return;
     const uint32_t per_cta = CTA_WARPS * WARP_MBS;
-    static int sm_count[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && sm_count[dev] == 0) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t resident = (uint32_t)(dev >= 0 && dev < 64 && sm_count[dev] > 0 ? sm_count[dev] : 148) * (32u / CTA_WARPS);  // 32 warps per SM
-    uint32_t grid = (n_mbs + per_cta - 1) / per_cta;
+    uint32_t grid = (n_mbs + per_cta * kTilesPerWarp - 1) / (per_cta * kTilesPerWarp);
     if (kPersistent) {
-        grid = min(grid, resident);
+        static int sm_count[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && sm_count[dev] == 0) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+        const uint32_t resident = (uint32_t)(dev >= 0 && dev < 64 && sm_count[dev] > 0 ? sm_count[dev] : 148) * (32u / CTA_WARPS);
+        grid = min((n_mbs + per_cta - 1) / per_cta, resident);
         cudaMemsetAsync(pools.work_counter, 0, sizeof(uint32_t), stream);  // tiles beyond the grid's first ones
     }
-    recon_tile_kernel<<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+    // pitches of the standard formats (context.cu: pitch_y = 16*mbw + 64, pitch_c = round_up(8*mbw + 32, 16))
+    const uint32_t py = pools.pitch_y, pc = pools.pitch_c, pr = pools.rgba_pitch;
+    if (py == 416 && pc == 208 && pr == 1408)  // CIF 352x288
+        recon_tile_kernel<416, 208, 1408><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+    else if (py == 240 && pc == 128 && pr == 704)  // QCIF 176x144
+        recon_tile_kernel<240, 128, 704><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+    else if (py == 768 && pc == 384 && pr == 2816)  // 4CIF 704x576
+        recon_tile_kernel<768, 384, 2816><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+    else
+        recon_tile_kernel<0, 0, 0><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
 }
 
 }  // namespace h263dev
