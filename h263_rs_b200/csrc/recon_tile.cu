@@ -56,6 +56,7 @@ constexpr int kTilesPerWarp = H263_TILES_PER_WARP;
 constexpr int CTA_THREADS = CTA_WARPS * 32;
 constexpr int WARP_BLOCKS = WARP_MBS * 6;
 constexpr int RES_WORDS = 36;
+constexpr int EV_CAP = 96;       // events walked at once (one slot has at most 64); more are walked in chunks
 constexpr int SLOT_FLOATS = 68;  // 64 + 4 pad: 16 B aligned, the four slots of a pass start 4 banks apart
 
 // per-macroblock flags (WarpSmem.mb[][3])
@@ -76,6 +77,11 @@ struct __align__(16) WarpSmem {
                                        // that holds the first source pixel of the block's row 0
     uint32_t bf[WARP_BLOCKS];          // per block: BF_* flags
     uint32_t meta[WARP_BLOCKS];        // per block: cls[2:0] | slot[7:3] | dcres[31:16]
+    uint32_t evbuf[EV_CAP];            // walked events of the slots in flight: lin[5:0] | dropped[15] | value[31:16]
+    uint32_t sstart[WARP_BLOCKS];      // per slot: index of its first event among the warp's events
+    uint32_t slotinfo[WARP_BLOCKS];    // per slot, gathered by the walk: rows[7:0] | column > 0 [8] | overflow [9]
+    uint32_t slotcls[WARP_BLOCKS];     // per slot after classification: rows to transform[7:0] | cls[10:8] | has_dc[11]
+    uint32_t order[WARP_BLOCKS];       // slots of the chunk sorted by rows to transform (most first)
 };
 
 struct TileSmem {
@@ -281,12 +287,19 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             }
         }
 
-        // coded blocks -> slots (block order)
+        // coded blocks -> slots (block order); their events form one sequence per warp
         const bool coded = nev > 0;
         const uint32_t coded_mask = __ballot_sync(FULL, coded);
         const int pos = __popc(coded_mask & lt_mask);
         n_slots = __popc(coded_mask);
+        uint32_t ev_incl = nev;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(FULL, ev_incl, d);
+            if (lane >= d) ev_incl += x;
+        }
         if (coded) {
+            W.sstart[pos] = ev_incl - nev;
             // events of the blocks before this one inside the macroblock
             const uint32_t n0 = (w2 >> 16) & 0xFF, n1 = w2 >> 24, n2 = w3 & 0xFF, n3 = (w3 >> 8) & 0xFF, n4 = (w3 >> 16) & 0xFF;
             uint32_t before = 0;
@@ -309,96 +322,158 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
     }
     __syncwarp();
 
-    // ================= phases 1 + 2: 4 slots per pass, 8 lanes per slot ============================
+    // ================= phases 1 + 2, per chunk of slots whose events fit the event buffer ==========
+    // (one chunk unless the four macroblocks hold more than EV_CAP events)
     {
         const float bt0 = S.basis[0 * 8 + t], bt1 = S.basis[1 * 8 + t], bt2 = S.basis[2 * 8 + t], bt3 = S.basis[3 * 8 + t],
                     bt4 = S.basis[4 * 8 + t], bt5 = S.basis[5 * 8 + t], bt6 = S.basis[6 * 8 + t], bt7 = S.basis[7 * 8 + t];
         float* c = W.coef[g];
-        for (int si0 = 0; si0 < n_slots; si0 += 4) {
-            const int si = si0 + g;
-            const bool valid = si < n_slots;
-            // lane t clears row t of the slot
-            *reinterpret_cast<float4*>(c + t * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(c + t * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-            const uint2 sd = valid ? W.slotdesc[si] : make_uint2(0u, 0u);
-            const int nev = (int)(sd.y & 0xFF), quant = (int)((sd.y >> 8) & 31);
-            const bool wide = (sd.y >> 13) & 1u, inter = (sd.y >> 14) & 1u;
-            const uint32_t blk = (sd.y >> 16) & 0xFFu, code = sd.y >> 24;
-            const h263cu_event* ev = events + sd.x;
-            const int q2 = 2 * quant, qc = quant - 1 + (quant & 1);
+        // lane = slot for the per-slot steps
+        const bool is_slot = lane < n_slots;
+        const uint2 my_sd = is_slot ? W.slotdesc[lane] : make_uint2(0u, 0u);
+        const uint32_t my_start = is_slot ? W.sstart[lane] : 0xFFFFFFFFu;
+        const uint32_t my_end = my_start + (my_sd.y & 0xFFu);
+        int s_lo = 0;
+        uint32_t e_lo = 0;
+        while (s_lo < n_slots) {
+            // slots of this chunk: the longest run starting at s_lo whose events fit the buffer
+            // (a slot with more events than the buffer holds -- a malformed record, real blocks have at most
+            // 64 -- is walked as far as the buffer goes: its index is past 63 by then and it is dropped)
+            const int s_hi = max(s_lo + 1, s_lo + __popc(__ballot_sync(FULL, is_slot && lane >= s_lo && my_end - e_lo <= (uint32_t)EV_CAP)));
+            const bool in_chunk = lane >= s_lo && lane < s_hi;
+            const uint32_t e_end = __shfl_sync(FULL, my_end, s_hi - 1);
+            const uint32_t e_hi = min(e_end, e_lo + (uint32_t)EV_CAP);
+            if (in_chunk) W.slotinfo[lane] = 0u;
             __syncwarp();
 
-            // ---- phase 1: the lanes take one event each; the zig-zag index is a prefix sum of run + 1
-            int next = inter ? 0 : 1;  // intra: the DC occupies zig-zag index 0 (rle.rs:117-121)
-            uint32_t info = 0;         // rows[7:0] | column > 0 [8] | zig-zag overflow [9]
-            const int nevmax = __reduce_max_sync(FULL, nev);
-            for (int e0 = 0; e0 < nevmax; e0 += 8) {
-                const int e = e0 + t;
-                const bool act = e < nev;
-                int run = 0, val = 0;
+            // ---- phase 1: lane = event.  The zig-zag index is a segmented prefix sum of run + 1 over the
+            // events of a slot (rle.rs:117-135); dequantise and park (position, value) in the event buffer.
+            uint32_t carry = 0;  // running sum of the slot that continues from the previous round
+            for (uint32_t eb = e_lo; eb < e_hi; eb += 32) {
+                const uint32_t e = eb + lane;
+                const bool act = e < e_hi;
+                // which slot: slots whose first event lies in this round mark their head
+                const bool head = in_chunk && my_start >= eb && my_start < eb + 32;
+                const uint32_t heads = __reduce_or_sync(FULL, head ? 1u << (my_start - eb) : 0u);
+                const int n_before = __popc(__ballot_sync(FULL, in_chunk && my_start < eb));
+                const uint32_t below = heads & (0xFFFFFFFFu >> (31 - lane));
+                const int slot = s_lo + n_before - 1 + __popc(below);
+                const int seg = below ? 31 - __clz(below) : -1;  // lane where my slot's events start in this round
+                int v = 0, val = 0;
+                bool inter = false;
                 if (act) {
-                    if (!wide) {
-                        const uint32_t u = __ldg(ev + e);
+                    const uint2 sd = W.slotdesc[slot];
+                    const uint32_t k = e - W.sstart[slot];
+                    const int quant = (int)((sd.y >> 8) & 31u);
+                    inter = (sd.y >> 14) & 1u;
+                    int run;
+                    if (!((sd.y >> 13) & 1u)) {
+                        const uint32_t u = __ldg(events + sd.x + k);
                         run = (int)(u >> 10);
-                        val = dequant_narrow(((int)(u << 22)) >> 22, q2, qc);
+                        val = dequant_narrow(((int)(u << 22)) >> 22, 2 * quant, quant - 1 + (quant & 1));
                     } else {
-                        run = __ldg(ev + 2 * e) & 63;
-                        val = dequant((int16_t)__ldg(ev + 2 * e + 1), quant);
+                        run = __ldg(events + sd.x + 2 * k) & 63;
+                        val = dequant((int16_t)__ldg(events + sd.x + 2 * k + 1), quant);
                     }
+                    v = run + 1;
                 }
-                int s = act ? run + 1 : 0;
-                int x = __shfl_up_sync(FULL, s, 1, 8);
-                if (t >= 1) s += x;
-                x = __shfl_up_sync(FULL, s, 2, 8);
-                if (t >= 2) s += x;
-                x = __shfl_up_sync(FULL, s, 4, 8);
-                if (t >= 4) s += x;
-                const int idx = next + s - 1;
-                next += __shfl_sync(FULL, s, 7, 8);
+                const int seg0 = max(seg, 0);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int x = __shfl_up_sync(FULL, v, d);
+                    if (lane - d >= seg0) v += x;
+                }
+                if (seg < 0) v += (int)carry;
+                carry = (uint32_t)__shfl_sync(FULL, v, 31);
                 if (act) {
+                    const int idx = (inter ? 0 : 1) + v - 1;  // intra: the DC occupies zig-zag index 0 (rle.rs:117-121)
+                    uint32_t bits, ent;
                     if (idx < 64) {
                         const int lin = S.dezigzag[idx];
-                        c[lin] = (float)val;
-                        info |= (1u << (lin >> 3)) | ((lin & 7) ? 0x100u : 0u);
+                        ent = (uint32_t)lin | ((uint32_t)val << 16);
+                        bits = (1u << (lin >> 3)) | ((lin & 7) ? 0x100u : 0u);
                     } else {
-                        info |= 0x200u;  // the whole block stays Zero, DC included (rle.rs:125-127)
+                        ent = 0x8000u;  // the whole block stays Zero, DC included (rle.rs:125-127)
+                        bits = 0x200u;
                     }
+                    W.evbuf[e - e_lo] = ent;
+                    atomicOr(&W.slotinfo[slot], bits);
                 }
             }
-            info |= __shfl_xor_sync(FULL, info, 1);
-            info |= __shfl_xor_sync(FULL, info, 2);
-            info |= __shfl_xor_sync(FULL, info, 4);
             __syncwarp();
-            const bool ovf = (info & 0x200u) != 0, col = (info & 0x100u) != 0;
-            const uint32_t rows = info & 0xFFu;
-            const bool has_dc = !inter && code != 0 && !ovf;  // false for padding groups (code == 0)
-            const int dcv = intradc_level((int)code);
-            int cls, dcres = 0;
-            uint32_t R = 0;
-            if (ovf || (!rows && !has_dc)) {
-                cls = CLS_ZERO;
-            } else if (!(rows & 0xFEu) && !col) {
-                cls = CLS_DC;
-                dcres = round_residual_dc(has_dc ? (float)dcv : c[0]);
-            } else {
-                cls = col ? CLS_FULL : CLS_VERT;
-                R = rows | (has_dc ? 1u : 0u);
-                if (has_dc && t == 0) c[0] = (float)dcv;
-            }
-            if (valid && t == 0) W.meta[blk] = (uint32_t)cls | ((uint32_t)si << 3) | ((uint32_t)dcres << 16);
 
-            // ---- phase 2: transform, lane t = column i of the block -------------------------------
-            // Per row y that holds a coefficient in ANY of the four slots (warp-uniform skip otherwise):
-            //   row pass    t[y][i] = sum_x c[y][x] * B[x][i], ascending x (idct_1d, idct.rs:52-65), pre-divided
-            //               by 4 (exact), which takes the /4 of idct.rs:189 out of the 64-output rounding
-            //   column pass out[i][j] += t[y][i] * B[y][j] for the 8 pixel rows j, ascending y; B[y][j] are
-            //               compile-time constants, t[y][i] never leaves the register
-            // A slot that has no coefficient in row y reads zeros there (the slot was cleared), so its terms
-            // are +-0 and change nothing -- skipping all-zero rows is exact, computing them is too.
-            const bool vert = cls == CLS_VERT;
-            const uint32_t U = __reduce_or_sync(FULL, R);
+            // ---- classification, lane = slot (rle.rs:94-171) ----
+            int key = 4;
+            if (in_chunk) {
+                const uint32_t info = W.slotinfo[lane];
+                const bool inter = (my_sd.y >> 14) & 1u;
+                const uint32_t blk = (my_sd.y >> 16) & 0xFFu, code = my_sd.y >> 24;
+                const bool ovf = (info & 0x200u) != 0, col = (info & 0x100u) != 0;
+                const uint32_t rows = info & 0xFFu;
+                const bool has_dc = !inter && code != 0 && !ovf;
+                int cls, dcres = 0;
+                uint32_t R = 0;
+                if (ovf || (!rows && !has_dc)) {
+                    cls = CLS_ZERO;
+                } else if (!(rows & 0xFEu) && !col) {
+                    cls = CLS_DC;
+                    // Dc(level): the intra DC, or the one coefficient an inter block put on index 0
+                    const int dc = has_dc ? intradc_level((int)code) : (int)W.evbuf[my_start - e_lo] >> 16;
+                    dcres = round_residual_dc((float)dc);
+                } else {
+                    cls = col ? CLS_FULL : CLS_VERT;
+                    R = rows | (has_dc ? 1u : 0u);
+                }
+                W.meta[blk] = (uint32_t)cls | ((uint32_t)lane << 3) | ((uint32_t)dcres << 16);
+                W.slotcls[lane] = R | ((uint32_t)cls << 8) | (has_dc ? 0x800u : 0u);
+                const int n = __popc(R);
+                key = n >= 4 ? 0 : (n >= 2 ? 1 : (n == 1 ? 2 : 3));
+            }
+            // slots that need the transform first, those with many rows before those with few, so that the
+            // four slots of a pass cost about the same
+            int pos = s_lo, n_need = 0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const uint32_t b = __ballot_sync(FULL, key == j);
+                if (j < key) pos += __popc(b);
+                if (j == key) pos += __popc(b & lt_mask);
+                n_need += __popc(b);
+            }
+            if (key < 3) W.order[pos] = (uint32_t)lane;
             __syncwarp();
-            if (U) {
+
+            // ---- phase 2: 4 slots per pass, 8 lanes per slot, lane t = column i of the block ---------
+            for (int si0 = s_lo; si0 < s_lo + n_need; si0 += 4) {
+                const int si = si0 + g;
+                const bool valid = si < s_lo + n_need;
+                const int sl = valid ? (int)W.order[si] : 0;
+                const uint32_t sc = valid ? W.slotcls[sl] : 0u;
+                const uint32_t R = sc & 0xFFu;
+                const bool vert = ((sc >> 8) & 7u) == CLS_VERT;
+                const uint2 sd = W.slotdesc[sl];
+                const int nev = valid ? (int)(sd.y & 0xFFu) : 0;
+                const uint32_t first = W.sstart[sl] - e_lo;
+                // lane t clears row t of the slot, then the slot's events are scattered into it
+                *reinterpret_cast<float4*>(c + t * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(c + t * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int nevmax = __reduce_max_sync(FULL, nev);
+                __syncwarp();
+                for (int k = t; k < nevmax; k += 8) {
+                    if (k < nev) {
+                        const uint32_t ent = W.evbuf[first + k];
+                        c[ent & 63u] = (float)((int)ent >> 16);
+                    }
+                }
+                if ((sc & 0x800u) && t == 0) c[0] = (float)intradc_level((int)(sd.y >> 24));
+                // Per row y that holds a coefficient in ANY of the four slots (warp-uniform skip otherwise):
+                //   row pass    t[y][i] = sum_x c[y][x] * B[x][i], ascending x (idct_1d, idct.rs:52-65), pre-divided
+                //               by 4 (exact), which takes the /4 of idct.rs:189 out of the 64-output rounding
+                //   column pass out[i][j] += t[y][i] * B[y][j] for the 8 pixel rows j, ascending y; B[y][j] are
+                //               compile-time constants, t[y][i] never leaves the register
+                // A slot that has no coefficient in row y reads zeros there (the slot was cleared), so its terms
+                // are +-0 and change nothing -- skipping all-zero rows is exact, computing them is too.
+                const uint32_t U = __reduce_or_sync(FULL, R);
+                __syncwarp();
                 float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int y = 0; y < 8; y++) {
@@ -422,15 +497,17 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     // pixel (x = t, y = j): residual row j of the slot, 16-bit lane of column t in the lane
                     // order of phase 3, (r0,r2) (r1,r3) (r4,r6) (r5,r7)
                     const float m = vert ? H263_B00 : 1.0f;
-                    uint16_t* rrow = reinterpret_cast<uint16_t*>(&W.res[si][0]) + ((t & 1) + 2 * (t >> 2)) * 2 + ((t >> 1) & 1);
+                    uint16_t* rrow = reinterpret_cast<uint16_t*>(&W.res[sl][0]) + ((t & 1) + 2 * (t >> 2)) * 2 + ((t >> 1) & 1);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const int r = round_q(acc[j], m);
                         rrow[j * 8] = (uint16_t)(int16_t)max(min(r, 255), -256);
                     }
                 }
+                __syncwarp();  // the coefficient slots are reused by the next pass
             }
-            __syncwarp();  // the coefficient slots are reused by the next pass
+            s_lo = s_hi;
+            e_lo = e_end;
         }
     }
 
