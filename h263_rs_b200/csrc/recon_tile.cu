@@ -156,11 +156,18 @@ struct CT {
 };
 // chroma terms with the -16 luma offset and the rounding constant folded in:
 //   R = (76309*y + r) >> 16 with r = 104597*(cr-128) + 32768 - 16*76309, etc.
-__device__ __forceinline__ CT chroma_terms_folded(int cb, int cr) {
+// The multipliers are passed in registers (see opaque()): a product with an immediate multiplier
+// AND an immediate addend does not encode, and the compiler would otherwise materialise the
+// multiplier once per use.
+__device__ __forceinline__ int opaque(int v) {
+    asm("" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ CT chroma_terms_folded(int cb, int cr, int kr, int kg, int kb) {
     CT t;
-    t.r = cr * 104597 + (32768 - 128 * 104597 - 16 * 76309);
-    t.g = cr * -53279 + (cb * -25675 + (32768 + 128 * 53279 + 128 * 25675 - 16 * 76309));
-    t.b = cb * 132201 + (32768 - 128 * 132201 - 16 * 76309);
+    t.r = cr * kr + (32768 - 128 * 104597 - 16 * 76309);
+    t.g = cr * kg + (cb * -25675 + (32768 + 128 * 53279 + 128 * 25675 - 16 * 76309));
+    t.b = cb * kb + (32768 - 128 * 132201 - 16 * 76309);
     return t;
 }
 __device__ __forceinline__ uint32_t rgba_px(int y, const CT& t) {
@@ -229,8 +236,9 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         const PicDev& P = pics[pic];
         const int mbx = (w1 >> 16) & 0xFF, mby = w1 >> 24;
         const bool inter = (w2 & H263CU_MB_INTER) != 0, wide = (w2 & H263CU_MB_WIDE) != 0;
-        const uint32_t nev = !bvalid ? 0u : (bb < 2 ? (w2 >> (16 + 8 * bb)) & 0xFFu : (w3 >> (8 * (bb - 2))) & 0xFFu);
-        const uint32_t code = inter ? 0u : (bb < 4 ? byte_of(w4, bb) : byte_of(w5, bb - 4));
+        // nev[6] = bytes 2..7 of (w2, w3); intradc[6] = bytes 0..5 of (w4, w5)
+        const uint32_t nev = bvalid ? __byte_perm(w2, w3, 0x4440u + (uint32_t)bb + 2u) & 0xFFu : 0u;
+        const uint32_t code = inter ? 0u : __byte_perm(w4, w5, 0x4440u + (uint32_t)bb) & 0xFFu;
 
         // motion: source offset, alignment and half-pel flags of this block
         uint32_t boff = 0, bflags = 0;
@@ -239,8 +247,8 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             uint32_t base;
             bool in_range;
             if (bb < 4) {
-                const uint32_t mvw = bb < 2 ? (w4 >> (16 * bb)) : (w5 >> (16 * (bb - 2)));
-                mvx = (int8_t)(mvw & 0xFF), mvy = (int8_t)((mvw >> 8) & 0xFF);
+                // mv[bb] = bytes 2bb, 2bb+1 of (w4, w5), sign-extended
+                mvx = (int)(int8_t)__byte_perm(w4, w5, 0x4440u + 2u * (uint32_t)bb), mvy = (int)(int8_t)__byte_perm(w4, w5, 0x4441u + 2u * (uint32_t)bb);
                 in_range = mvx >= -32 && mvx <= 31 && mvy >= -32 && mvy <= 31;
                 sx = mbx * 16 + (bb & 1) * 8 + (mvx >> 1), sy = mby * 16 + (bb >> 1) * 8 + (mvy >> 1);
                 pitch = PY ? PY : P.pitch_y, base = P.ref_y4;
@@ -298,16 +306,10 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             const uint32_t x = __shfl_up_sync(FULL, ev_incl, d);
             if (lane >= d) ev_incl += x;
         }
+        // events of the blocks before this one inside the macroblock
+        const uint32_t before = (ev_incl - nev) - __shfl_sync(FULL, ev_incl - nev, bm * 6);
         if (coded) {
             W.sstart[pos] = ev_incl - nev;
-            // events of the blocks before this one inside the macroblock
-            const uint32_t n0 = (w2 >> 16) & 0xFF, n1 = w2 >> 24, n2 = w3 & 0xFF, n3 = (w3 >> 8) & 0xFF, n4 = (w3 >> 16) & 0xFF;
-            uint32_t before = 0;
-            before += bb > 0 ? n0 : 0;
-            before += bb > 1 ? n1 : 0;
-            before += bb > 2 ? n2 : 0;
-            before += bb > 3 ? n3 : 0;
-            before += bb > 4 ? n4 : 0;
             const uint32_t first = P.first_event + w0 + (wide ? 2 * before : before);
             const uint32_t quant = (w2 >> 8) & 31u;
             W.slotdesc[pos] = make_uint2(first, nev | (quant << 8) | (wide ? 1u << 13 : 0u) | (inter ? 1u << 14 : 0u) |
@@ -458,13 +460,19 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 *reinterpret_cast<float4*>(c + t * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int nevmax = __reduce_max_sync(FULL, nev);
                 __syncwarp();
-                for (int k = t; k < nevmax; k += 8) {
-                    if (k < nev) {
+                if (t < nev) {
+                    const uint32_t ent = W.evbuf[first + t];
+                    c[ent & 63u] = (float)((int)ent >> 16);
+                }
+                if (nevmax > 8) {  // rare: more than 8 events in a slot of this pass
+                    for (int k = t + 8; k < nev; k += 8) {
                         const uint32_t ent = W.evbuf[first + k];
                         c[ent & 63u] = (float)((int)ent >> 16);
                     }
                 }
-                if ((sc & 0x800u) && t == 0) c[0] = (float)intradc_level((int)(sd.y >> 24));
+                if (sc & 0x800u) {
+                    if (t == 0) c[0] = (float)intradc_level((int)(sd.y >> 24));
+                }
                 // Per row y that holds a coefficient in ANY of the four slots (warp-uniform skip otherwise):
                 //   row pass    t[y][i] = sum_x c[y][x] * B[x][i], ascending x (idct_1d, idct.rs:52-65), pre-divided
                 //               by 4 (exact), which takes the /4 of idct.rs:189 out of the 64-output rounding
@@ -759,13 +767,14 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             if (flags & MBF_RGBA) {
                 const uint32_t rgba_pitch = PR ? PR : mv.y;
                 uint8_t* o = pools.rgba + (size_t)ma.z * 16 + (size_t)(rg * 4) * rgba_pitch + (size_t)(h * 32);
+                const int kr = opaque(104597), kg = opaque(-53279), kb = opaque(132201);
 #pragma unroll
                 for (int cr2 = 0; cr2 < 2; cr2++) {
                     // chroma row cr2 serves luma rows 2*cr2, 2*cr2+1; sample j serves pixels 2j, 2j+1
-                    const CT t0 = chroma_terms_folded((int)(ce[0][cr2] & 0xFFFFu), (int)(ce[1][cr2] & 0xFFFFu));
-                    const CT t1 = chroma_terms_folded((int)(co[0][cr2] & 0xFFFFu), (int)(co[1][cr2] & 0xFFFFu));
-                    const CT t2 = chroma_terms_folded((int)(ce[0][cr2] >> 16), (int)(ce[1][cr2] >> 16));
-                    const CT t3 = chroma_terms_folded((int)(co[0][cr2] >> 16), (int)(co[1][cr2] >> 16));
+                    const CT t0 = chroma_terms_folded((int)(ce[0][cr2] & 0xFFFFu), (int)(ce[1][cr2] & 0xFFFFu), kr, kg, kb);
+                    const CT t1 = chroma_terms_folded((int)(co[0][cr2] & 0xFFFFu), (int)(co[1][cr2] & 0xFFFFu), kr, kg, kb);
+                    const CT t2 = chroma_terms_folded((int)(ce[0][cr2] >> 16), (int)(ce[1][cr2] >> 16), kr, kg, kb);
+                    const CT t3 = chroma_terms_folded((int)(co[0][cr2] >> 16), (int)(co[1][cr2] >> 16), kr, kg, kb);
 #pragma unroll
                     for (int rr = 0; rr < 2; rr++) {
                         const RowSum& L = ly[cr2 * 2 + rr];
