@@ -67,17 +67,20 @@ def host_threads():
 
 
 # ---------------------------------------------------------------------------- workload
-def generate_streams(n_streams, n_pictures, seed0, threads):
-    """Returns per-stream (blob, off, len) of synthetic CIF streams, generated in parallel
+def generate_streams(stream_ids, n_pictures, threads, w=W, h=H, **overrides):
+    """Returns per-stream (blob, off, len) of synthetic streams, one per GLOBAL stream id (the id
+    is the generator seed; every fourth stream uses full-range vectors), generated in parallel
     (ctypes releases the GIL inside the generator)."""
     from h263_rs_b200 import synth
 
     def one(s):
-        p = synth.default_params(W, H, n_pictures, seed0 + s, mv_mode=0 if s % 4 else 1)
+        kw = dict(mv_mode=0 if s % 4 else 1)
+        kw.update(overrides)
+        p = synth.default_params(w, h, n_pictures, int(s), **kw)
         return synth.make_stream_blob(p)
 
     with ThreadPoolExecutor(max_workers=threads) as ex:
-        return list(ex.map(one, range(n_streams)))
+        return list(ex.map(one, list(stream_ids)))
 
 
 def workload_description(streams_per_gpu, unique, n_gpus):
@@ -226,7 +229,7 @@ def run_reference(args, rank):
     n_streams = args.streams
     total = args.warmup + args.steps + 1
     t0 = time.time()
-    blobs = generate_streams(n_streams, total, 0, threads)
+    blobs = generate_streams(range(n_streams), total, threads)
     gen_s = time.time() - t0
     secs = cpu_steps(blobs, range(total), threads, n_streams)
     timed = secs[1 + args.warmup :]
@@ -255,7 +258,7 @@ def run_reference(args, rank):
 def run_ours(args, rank, world, local_rank, dist):
     import torch
 
-    from h263_rs_b200 import _lib, api, frontend
+    from h263_rs_b200 import _lib, api, frontend, shard
 
     threads = max(1, host_threads() // max(world, 1))
     S = args.streams
@@ -267,7 +270,9 @@ def run_ours(args, rank, world, local_rank, dist):
 
     # ---- setup (untimed): generate, parse (threaded), stage in pinned memory, upload
     t0 = time.time()
-    blobs = generate_streams(U, total, rank * S, threads)
+    # shard by stream: this rank owns the global streams s with s % world == rank (shard.py)
+    gids = shard.shard_streams(S * world, world, rank)
+    blobs = generate_streams(gids[:U], total, threads)
     gen_s = time.time() - t0
     parsers = [frontend.Parser(1) for _ in range(S)]
     host_steps, steps = [], []
@@ -310,18 +315,10 @@ def run_ours(args, rank, world, local_rank, dist):
         ctx.sync()
 
     def reduce_max(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.reduce_max(dist, v, "cuda")
 
     def reduce_sum(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return shard.reduce_sum(dist, v, "cuda")
 
     # ---- value: side info resident in HBM, CUDA-event timed, per-launch kernel timing
     sampler = ClockSampler(local_rank)
@@ -403,6 +400,7 @@ def run_ours(args, rank, world, local_rank, dist):
         }
         if not args.skip_extras:
             extras["single_stream_config2"] = single_stream(api, frontend, local_rank)
+            extras["config4_4cif_deblock"] = config4_deblock(api, frontend, local_rank, threads)
 
     for st in steps:
         L.h263cu_step_free(ctx.h, st)
@@ -488,6 +486,53 @@ def single_stream(api, frontend, device):
     fps = (n - 20) / (ms * 1e-3)
     return {"frames_per_s": fps, "value": fps * W * H / 1e6, "unit": UNIT, "pictures": n,
             "note": "one dependent kernel launch per picture (396 macroblocks): latency bound, not a roofline case"}
+
+
+def config4_deblock(api, frontend, device, threads, n_streams=256, n_steps=6):
+    """BASELINE.json configs[3]: 256 concurrent 4CIF 704x576 streams, deblocking flag set, vectors
+    biased across the picture borders; recon kernel + fused deblock/RGBA kernel per step."""
+    from h263_rs_b200 import _lib
+
+    w, h = 704, 576
+    blobs = generate_streams(range(n_streams), 1 + n_steps, threads, w, h, mv_mode=2, deblock_flag=1)
+    ctx = api.Context(device, n_streams, w, h)
+    parsers = [frontend.Parser(1) for _ in range(n_streams)]
+    steps = []
+    for t in range(1 + n_steps):
+        packets = [b[int(off[t]) : int(off[t]) + int(ln[t])].tobytes() for b, off, ln in blobs]
+        pics, mbs, events, errs, _ = frontend.parse_step(parsers, packets, np.arange(n_streams, dtype=np.uint32), threads,
+                                                         mb_cap=n_streams * 44 * 36)
+        assert not errs.any()
+        steps.append(ctx.step_upload(pics, mbs, events))
+    flags = _lib.OUT_RGBA | _lib.OUT_DEBLOCK
+    ctx.sync()
+    for st in steps[:3]:
+        ctx.step_run(st, flags)
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    ctx.timer_start()
+    for st in steps[3:]:
+        ctx.step_run(st, flags)
+    ms = ctx.timer_stop()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    # parity: stream 0 against the oracle with the deblocking post-filter
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_decode_stream
+
+    b, off, ln = blobs[0]
+    ref = oracle_decode_stream([b[int(off[t]) : int(off[t]) + int(ln[t])].tobytes() for t in range(1 + n_steps)], deblock=True)
+    ok = bool(np.array_equal(ctx.read_rgba(0), ref[-1]["rgba"]))
+    for st in steps:
+        ctx.step_free(st)
+    ctx.close()
+    n = n_steps - 2
+    px = n_streams * w * h * n
+    return {"value": px / (ms * 1e-3) / 1e6, "unit": UNIT, "frames_per_s": n_streams * n / (ms * 1e-3), "streams": n_streams,
+            "picture": "704x576", "ms_per_step": ms / n, "recon_ms_per_step": prof["recon_ms"] / max(prof["recon_launches"], 1),
+            "deblock_rgba_ms_per_step": prof["deblock_ms"] / max(prof["deblock_launches"], 1),
+            "bit_exact_vs_oracle_stream0": ok,
+            "note": "P pictures, deblock::deblock on Y/Cb/Cr (QUANT_TO_STRENGTH[PQUANT]) fused with RGBA in a second kernel"}
 
 
 def measured_peaks():
