@@ -178,7 +178,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     const bool want_deblock = want_rgba && (out_flags & H263CU_OUT_DEBLOCK) != 0;
     c->stamp++;
     uint32_t max_w = 0, max_h = 0;
-    bool tiled = true;
+    bool tiled = true, aligned16 = true;
     for (uint32_t i = 0; i < n; i++) {
         const h263cu_pic& p = s->pics[i];
         if (p.stream >= c->max_streams) return H263CU_ERR_CAPACITY;
@@ -199,7 +199,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         max_w = std::max<uint32_t>(max_w, p.width);
         max_h = std::max<uint32_t>(max_h, p.height);
         // the tiled kernel needs MB-aligned pictures and references with a replicated border
-        if ((p.width | p.height) & 15) tiled = false;
+        if ((p.width | p.height) & 15) tiled = false, aligned16 = false;
         if ((p.flags & H263CU_PICFLAG_HAS_INTER) && !st.padded) tiled = false;
     }
     if (c->force_kernel == 1) tiled = false;
@@ -256,7 +256,10 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     if (c->profiling) prof_end(c, pa, pb, 0);
     if (want_deblock) {
         if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
-        launch_deblock_rgba(c->d_pics[slot], n, max_w, max_h, c->s_main);
+        if (aligned16 && c->force_kernel != 1)
+            launch_deblock_rgba_tile(c->d_pics[slot], n, max_w, max_h, c->s_main);
+        else
+            launch_deblock_rgba(c->d_pics[slot], n, max_w, max_h, c->s_main);
         c->launches++;
         if (c->profiling) prof_end(c, pa, pb, 1);
     }

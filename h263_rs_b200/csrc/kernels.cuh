@@ -58,6 +58,8 @@ constexpr int PAD_Y_COLS = 32, PAD_Y_ROWS = 16, PAD_C_COLS = 16, PAD_C_ROWS = 8;
 // Deblocking post-filter (per plane, per picture) fused with the RGBA conversion.
 // grid = (max tiles per picture, n_pics).
 void launch_deblock_rgba(const PicDev* pics, uint32_t n_pics, uint32_t max_w, uint32_t max_h, cudaStream_t stream);
+// deblock_tile.cu: the register-resident form for pictures whose sizes are multiples of 16
+void launch_deblock_rgba_tile(const PicDev* pics, uint32_t n_pics, uint32_t max_w, uint32_t max_h, cudaStream_t stream);
 
 // Stateless kernels behind h263cu_yuv420_to_rgba / h263cu_deblock (tight planes).
 void launch_yuv420_to_rgba(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, uint32_t w, uint32_t h,
