@@ -38,6 +38,11 @@ constexpr int WARP_MBS = 4;      // macroblocks per warp
 #ifndef H263_LDG64
 #define H263_LDG64 0
 #endif
+// Ablation builds for time attribution (results are wrong by design): 1 = no event walk / transform,
+// 2 = no prediction loads (every macroblock treated as intra), 4 = no RGBA, 8 = no plane stores.
+#ifndef H263_ABLATE
+#define H263_ABLATE 0
+#endif
 #ifndef H263_MIN_CTAS
 #define H263_MIN_CTAS (32 / H263_CTA_WARPS)
 #endif
@@ -331,6 +336,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     bt4 = S.basis[4 * 8 + t], bt5 = S.basis[5 * 8 + t], bt6 = S.basis[6 * 8 + t], bt7 = S.basis[7 * 8 + t];
         float* c = W.coef[g];
         // lane = slot for the per-slot steps
+        if (H263_ABLATE & 1) n_slots = 0;
         const bool is_slot = lane < n_slots;
         const uint2 my_sd = is_slot ? W.slotdesc[lane] : make_uint2(0u, 0u);
         const uint32_t my_start = is_slot ? W.sstart[lane] : 0xFFFFFFFFu;
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         const int mbi = unit_ok ? mbq : 0;
         const uint4 ma = *reinterpret_cast<const uint4*>(&W.mb[mbi][0]);
         const uint4 mv = *reinterpret_cast<const uint4*>(&W.mb[mbi][4]);
-        const uint32_t flags = unit_ok ? ma.w : 0u;
+        const uint32_t flags = (unit_ok ? ma.w : 0u) & ~((H263_ABLATE & 2) ? MBF_INTER : 0u) & ~((H263_ABLATE & 4) ? MBF_RGBA : 0u);
         const uint32_t pitch_y4 = PY ? PY / 4 : (mv.x & 0xFFFFu) >> 2, pitch_c4 = PC ? PC / 4 : mv.x >> 18;
         const int lb = ((rg >> 1) << 1) | h;  // luma block of this unit
         const int r0 = (rg & 1) * 4;          // first row of the unit inside its block
@@ -689,7 +695,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             cw[r][0] = __byte_perm(cy[r].e0, cy[r].o0, 0x6240);
             cw[r][1] = __byte_perm(cy[r].e1, cy[r].o1, 0x6240);
         }
-        if (unit_ok) {
+        if (unit_ok && !(H263_ABLATE & 8)) {
             uint8_t* py = pools.y + (size_t)(ma.x + (uint32_t)(rg * 4) * pitch_y4 + (uint32_t)(h * 2)) * 4;
             uint8_t* pc = (h ? pools.cr : pools.cb) + (size_t)(ma.y + (uint32_t)(rg * 2) * pitch_c4) * 4;
 #pragma unroll

@@ -83,7 +83,20 @@ def _packets(c):
     return synth.make_stream(c["w"], c["h"], c["n"], c["seed"], **kw), (0 if kw.get("flavour", 0) == 1 else 1)
 
 
-@pytest.mark.parametrize("case", STREAMS, ids=lambda c: c["id"])
+# small MB-aligned sizes: the register-resident deblock kernel's border cells, chroma planes too narrow
+# for a vertical edge (width 8 < 10, deblock.rs:228), single-row / single-column macroblock grids, and
+# every quantiser (= every filter strength of QUANT_TO_STRENGTH)
+SMALL_ALIGNED = [
+    dict(id="16x16", w=16, h=16, n=4, seed=21, mv_mode=1),
+    dict(id="32x16", w=32, h=16, n=4, seed=22, mv_mode=2),
+    dict(id="16x48", w=16, h=48, n=4, seed=23, mv_mode=1),
+    dict(id="48x32_q31", w=48, h=32, n=5, seed=24, mv_mode=2, qp_min=24, qp_max=31),
+    dict(id="64x64_q1", w=64, h=64, n=5, seed=25, mv_mode=1, qp_min=1, qp_max=3, pct_dquant=50),
+    dict(id="96x80_dense", w=96, h=80, n=4, seed=26, mean_events_x10=150, pct_cbp_inter=95, pct_cbp_intra=100, pct_intra=40),
+]
+
+
+@pytest.mark.parametrize("case", STREAMS + SMALL_ALIGNED, ids=lambda c: c["id"])
 def test_decode_next_picture_bit_exact(case):
     packets, opt = _packets(case)
     ref = oracle_decode_stream(packets, opt)
@@ -103,7 +116,7 @@ def test_decode_next_picture_bit_exact(case):
         assert np.array_equal(st.get_last_rgba(), ref[i]["rgba"]), (case["id"], i, "RGBA")
 
 
-@pytest.mark.parametrize("case", [STREAMS[0], STREAMS[2], STREAMS[6], STREAMS[7]], ids=lambda c: c["id"])
+@pytest.mark.parametrize("case", [STREAMS[0], STREAMS[2], STREAMS[6], STREAMS[7]] + SMALL_ALIGNED, ids=lambda c: c["id"])
 def test_deblocked_rgba_bit_exact(case):
     """recon -> deblock(plane, width, QUANT_TO_STRENGTH[pquant]) per plane -> RGBA; the
     reference frames stay un-deblocked (BASELINE.json config 4 composition)."""
