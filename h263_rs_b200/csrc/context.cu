@@ -75,11 +75,13 @@ struct h263cu_ctx {
     uint32_t rgba_parity = 0;
 
     cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_pics = nullptr;  // descriptor uploads: overlap the previous step's kernels
     // PicDev staging ring (pinned host + device)
     static constexpr int PIC_RING = 4;
     PicDev* h_pics[PIC_RING] = {};
     PicDev* d_pics[PIC_RING] = {};
-    cudaEvent_t pics_done[PIC_RING] = {};
+    cudaEvent_t pics_done[PIC_RING] = {};  // the kernels that read d_pics[i] have finished
+    cudaEvent_t pics_up[PIC_RING] = {};    // d_pics[i] is uploaded
     size_t pics_cap = 0;
     int pic_ring_pos = 0;
     // side-info ring used by h263cu_submit_step*
@@ -242,8 +244,11 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         st.rgba_slot = want_rgba ? (int8_t)rgba_ring : (int8_t)-1;
         st.padded = tiled;
     }
-    CU_TRY(cudaMemcpyAsync(c->d_pics[slot], hp, n * sizeof(PicDev), cudaMemcpyHostToDevice, c->s_main));
-    CU_TRY(cudaEventRecord(c->pics_done[slot], c->s_main));
+    // the descriptors travel on their own stream, so the copy overlaps the previous step's kernels
+    // (pics_done[slot] was waited for above: the kernels that read this ring slot four steps ago are done)
+    CU_TRY(cudaMemcpyAsync(c->d_pics[slot], hp, n * sizeof(PicDev), cudaMemcpyHostToDevice, c->s_pics));
+    CU_TRY(cudaEventRecord(c->pics_up[slot], c->s_pics));
+    CU_TRY(cudaStreamWaitEvent(c->s_main, c->pics_up[slot], 0));
     if (want_rgba) {
         // do not overwrite an RGBA ring slot that is still being read back
         CU_TRY(cudaStreamWaitEvent(c->s_main, c->rgba_read[rgba_ring], 0));
@@ -264,6 +269,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         if (c->profiling) prof_end(c, pa, pb, 1);
     }
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(c->pics_done[slot], c->s_main));
     if (want_rgba) {
         CU_TRY(cudaEventRecord(c->rgba_written[rgba_ring], c->s_main));
         c->rgba_parity++;
@@ -366,8 +372,11 @@ h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, 
     if (cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&c->s_pics, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
     for (int i = 0; i < h263cu_ctx::PIC_RING; i++)
-        if (cudaEventCreateWithFlags(&c->pics_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&c->pics_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->pics_up[i], cudaEventDisableTiming) != cudaSuccess)
+            return fail(H263CU_ERR_CUDA);
     for (int i = 0; i < 2; i++) {
         if (cudaEventCreateWithFlags(&c->ring_h2d_done[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ring_run_done[i], cudaEventDisableTiming) != cudaSuccess ||
@@ -391,11 +400,13 @@ void h263cu_destroy(h263cu_ctx* c) {
     if (c->s_main) cudaStreamSynchronize(c->s_main);
     if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
     if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+    if (c->s_pics) cudaStreamSynchronize(c->s_pics);
     for (int i = 0; i < 2; i++) free_step_buffers(&c->ring[i]);
     for (int i = 0; i < h263cu_ctx::PIC_RING; i++) {
         if (c->h_pics[i]) cudaFreeHost(c->h_pics[i]);
         if (c->d_pics[i]) cudaFree(c->d_pics[i]);
         if (c->pics_done[i]) cudaEventDestroy(c->pics_done[i]);
+        if (c->pics_up[i]) cudaEventDestroy(c->pics_up[i]);
     }
     for (int i = 0; i < 2; i++) {
         if (c->ring_h2d_done[i]) cudaEventDestroy(c->ring_h2d_done[i]);
@@ -420,6 +431,7 @@ void h263cu_destroy(h263cu_ctx* c) {
     if (c->s_main) cudaStreamDestroy(c->s_main);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    if (c->s_pics) cudaStreamDestroy(c->s_pics);
     delete c;
 }
 

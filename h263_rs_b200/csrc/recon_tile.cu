@@ -27,7 +27,7 @@ namespace {
 
 constexpr int WARP_MBS = 4;      // macroblocks per warp
 #ifndef H263_CTA_WARPS
-#define H263_CTA_WARPS 8
+#define H263_CTA_WARPS 4  // without the staging barrier a CTA is just a group of warps: 4 beat 8 by 1-2 % (shorter tails)
 #endif
 #ifndef H263_PERSISTENT
 #define H263_PERSISTENT 0
@@ -45,6 +45,22 @@ constexpr int WARP_MBS = 4;      // macroblocks per warp
 #endif
 #ifndef H263_MIN_CTAS
 #define H263_MIN_CTAS (32 / H263_CTA_WARPS)
+#endif
+// 1 = stage BASIS_TABLE / the de-zigzag map in shared memory behind a CTA barrier (versions up to v10);
+// 0 = read them from global memory (L1-resident, 320 bytes): no per-CTA staging, no barrier at all, so
+// a CTA's warps start on their record loads at once and small CTAs cost nothing extra.
+#ifndef H263_SMEM_TABLES
+#define H263_SMEM_TABLES 0
+#endif
+// L2 eviction priorities (createpolicy): bit 0 = RGBA stores evict_first (write-once output), bit 1 = plane
+// stores evict_last (the next step's prediction source), bit 2 = prediction loads evict_first (dead after use)
+#ifndef H263_L2_POLICY
+#define H263_L2_POLICY 0
+#endif
+// 1 = BT.601 through mad.wide: (y << 16) * 76309 + (term << 16) leaves (y * 76309 + term) >> 16 in the high
+// word, one instruction per channel instead of multiply-add + shift
+#ifndef H263_RGBA_WIDE
+#define H263_RGBA_WIDE 0
 #endif
 constexpr int CTA_WARPS = H263_CTA_WARPS;
 // Persistent warps drawing tiles from a global counter were measured SLOWER than one CTA per 32
@@ -91,9 +107,16 @@ struct __align__(16) WarpSmem {
 
 struct TileSmem {
     WarpSmem w[CTA_WARPS];
+#if H263_SMEM_TABLES
     float basis[64];
     uint8_t dezigzag[64];
+#endif
 };
+
+#if !H263_SMEM_TABLES
+__device__ const float g_basis[8][8] = H263_BASIS_TABLE;
+__device__ const uint8_t g_dezigzag[64] = H263_DEZIGZAG_LINEAR;
+#endif
 
 // compile-time copy of BASIS_TABLE: with y and j unrolled these fold into immediates of the column pass
 __device__ __forceinline__ constexpr float k_basis(int y, int j) {
@@ -180,10 +203,34 @@ __device__ __forceinline__ uint32_t rgba_px(int y, const CT& t) {
     return pack_sat(g, r, pack_sat(255, b, 0));
 }
 
+// The same through 64-bit multiply-adds: with y16 = y << 16 and the chroma terms held as term << 16,
+// y16 * 76309 + term64 = (y * 76309 + term) << 16 exactly, so the high word is the shifted channel.
+struct CT64 {
+    long long r, g, b;
+};
+__device__ __forceinline__ CT64 chroma_terms_wide(int cb16, int cr16, int kr, int kg, int kb) {
+    CT64 t;
+    t.r = (long long)cr16 * kr + ((long long)(32768 - 128 * 104597 - 16 * 76309) << 16);
+    t.g = (long long)cr16 * kg + ((long long)cb16 * -25675 + ((long long)(32768 + 128 * 53279 + 128 * 25675 - 16 * 76309) << 16));
+    t.b = (long long)cb16 * kb + ((long long)(32768 - 128 * 132201 - 16 * 76309) << 16);
+    return t;
+}
+__device__ __forceinline__ uint32_t rgba_px_wide(int y16, const CT64& t) {
+    const int r = (int)(((long long)y16 * 76309 + t.r) >> 32), g = (int)(((long long)y16 * 76309 + t.g) >> 32),
+              b = (int)(((long long)y16 * 76309 + t.b) >> 32);
+    return pack_sat(g, r, pack_sat(255, b, 0));
+}
+
 __device__ __forceinline__ void st_global_v8(uint8_t* p, const uint32_t (&v)[8]) {
+#if H263_L2_POLICY & 1
+    asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+#else
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
+#endif
 }
 
 __device__ __forceinline__ uint32_t splat_lo(uint32_t w) { return __byte_perm(w, 0, 0x0000); }
@@ -201,11 +248,13 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                       const h263cu_event* __restrict__ events, uint32_t n_mbs, int emit_rgba, const Pools pools) {
     __shared__ __align__(16) TileSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if H263_SMEM_TABLES
     if (tid < 64) {
         S.basis[tid] = c_basis[tid >> 3][tid & 7];
         S.dezigzag[tid] = c_dezigzag[tid];
     }
     __syncthreads();  // the only CTA-wide barrier: from here on every warp runs on its own
+#endif
     WarpSmem& W = S.w[warp];
     const int g = lane >> 3, t = lane & 7;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -332,8 +381,13 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
     // ================= phases 1 + 2, per chunk of slots whose events fit the event buffer ==========
     // (one chunk unless the four macroblocks hold more than EV_CAP events)
     {
-        const float bt0 = S.basis[0 * 8 + t], bt1 = S.basis[1 * 8 + t], bt2 = S.basis[2 * 8 + t], bt3 = S.basis[3 * 8 + t],
-                    bt4 = S.basis[4 * 8 + t], bt5 = S.basis[5 * 8 + t], bt6 = S.basis[6 * 8 + t], bt7 = S.basis[7 * 8 + t];
+#if H263_SMEM_TABLES
+        const float* const basis = S.basis;
+#else
+        const float* const basis = &g_basis[0][0];
+#endif
+        const float bt0 = basis[0 * 8 + t], bt1 = basis[1 * 8 + t], bt2 = basis[2 * 8 + t], bt3 = basis[3 * 8 + t],
+                    bt4 = basis[4 * 8 + t], bt5 = basis[5 * 8 + t], bt6 = basis[6 * 8 + t], bt7 = basis[7 * 8 + t];
         float* c = W.coef[g];
         // lane = slot for the per-slot steps
         if (H263_ABLATE & 1) n_slots = 0;
@@ -397,7 +451,11 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     const int idx = (inter ? 0 : 1) + v - 1;  // intra: the DC occupies zig-zag index 0 (rle.rs:117-121)
                     uint32_t bits, ent;
                     if (idx < 64) {
+#if H263_SMEM_TABLES
                         const int lin = S.dezigzag[idx];
+#else
+                        const int lin = g_dezigzag[idx];
+#endif
                         ent = (uint32_t)lin | ((uint32_t)val << 16);
                         bits = (1u << (lin >> 3)) | ((lin & 7) ? 0x100u : 0u);
                     } else {
@@ -775,6 +833,32 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 uint8_t* o = pools.rgba + (size_t)ma.z * 16 + (size_t)(rg * 4) * rgba_pitch + (size_t)(h * 32);
                 const int kr = opaque(104597), kg = opaque(-53279), kb = opaque(132201);
 #pragma unroll
+#if H263_RGBA_WIDE
+#pragma unroll
+                for (int cr2 = 0; cr2 < 2; cr2++) {
+                    uint32_t px[2][8];
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {  // pixels 0..3 use chroma samples 0, 1 (low lanes), 4..7 samples 2, 3
+                        const uint32_t cbe = ce[0][cr2], cre = ce[1][cr2], cbo = co[0][cr2], cro = co[1][cr2];
+                        const CT64 ta = half ? chroma_terms_wide((int)(cbe & 0xFFFF0000u), (int)(cre & 0xFFFF0000u), kr, kg, kb)
+                                             : chroma_terms_wide((int)(cbe << 16), (int)(cre << 16), kr, kg, kb);
+                        const CT64 tb = half ? chroma_terms_wide((int)(cbo & 0xFFFF0000u), (int)(cro & 0xFFFF0000u), kr, kg, kb)
+                                             : chroma_terms_wide((int)(cbo << 16), (int)(cro << 16), kr, kg, kb);
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++) {
+                            const RowSum& L = ly[cr2 * 2 + rr];
+                            const uint32_t le = half ? L.e1 : L.e0, lo = half ? L.o1 : L.o0;
+                            px[rr][half * 4 + 0] = rgba_px_wide((int)(le << 16), ta);
+                            px[rr][half * 4 + 1] = rgba_px_wide((int)(lo << 16), ta);
+                            px[rr][half * 4 + 2] = rgba_px_wide((int)(le & 0xFFFF0000u), tb);
+                            px[rr][half * 4 + 3] = rgba_px_wide((int)(lo & 0xFFFF0000u), tb);
+                        }
+                    }
+                    st_global_v8(o + (size_t)(cr2 * 2 + 0) * rgba_pitch, px[0]);
+                    st_global_v8(o + (size_t)(cr2 * 2 + 1) * rgba_pitch, px[1]);
+                }
+#else
+#pragma unroll
                 for (int cr2 = 0; cr2 < 2; cr2++) {
                     // chroma row cr2 serves luma rows 2*cr2, 2*cr2+1; sample j serves pixels 2j, 2j+1
                     const CT t0 = chroma_terms_folded((int)(ce[0][cr2] & 0xFFFFu), (int)(ce[1][cr2] & 0xFFFFu), kr, kg, kb);
@@ -796,6 +880,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                         st_global_v8(o + (size_t)(cr2 * 2 + rr) * rgba_pitch, px);
                     }
                 }
+#endif
             }
         }
     }
