@@ -68,7 +68,7 @@ SYMBOLS = [
     "h263cu_peek_picture", "h263cu_parse_picture", "h263cu_parse_step", "h263cu_device_count",
     "h263cu_create", "h263cu_destroy", "h263cu_device_of", "h263cu_alloc_pinned", "h263cu_free_pinned",
     "h263cu_step_upload", "h263cu_step_free", "h263cu_step_run", "h263cu_submit_step",
-    "h263cu_submit_step_readback", "h263cu_sync", "h263cu_stream_info", "h263cu_read_yuv", "h263cu_read_rgba",
+    "h263cu_submit_step_readback", "h263cu_decode_step", "h263cu_sync", "h263cu_stream_info", "h263cu_read_yuv", "h263cu_read_rgba",
     "h263cu_checksums", "h263cu_timer_start", "h263cu_timer_stop", "h263cu_launch_count",
     "h263cu_profile_enable", "h263cu_profile_read",
     "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength", "h263cu_synth_default_params",
@@ -120,6 +120,7 @@ def lib():
         L.h263cu_step_run.argtypes = [vp, vp, u32]
         L.h263cu_submit_step.argtypes = [vp, vp, u32, vp, u32, vp, u32, u32]
         L.h263cu_submit_step_readback.argtypes = [vp, vp, u32, vp, u32, vp, u32, u32, vp, vp]
+        L.h263cu_decode_step.argtypes = [vp, vp, vp, vp, vp, u32, i32, u32, vp, u64, vp, C.POINTER(u32)]
         L.h263cu_sync.argtypes = [vp]
         L.h263cu_stream_info.argtypes = [vp, u32] + [C.POINTER(u32)] * 5
         L.h263cu_read_yuv.argtypes = [vp, u32, vp, vp, vp]

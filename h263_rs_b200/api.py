@@ -235,10 +235,10 @@ class BatchDecoder:
     """n independent streams decoded in lock step: one picture per stream per step."""
 
     def __init__(self, n_streams, max_width, max_height, decoder_options=SORENSON_SPARK_BITSTREAM, device=0,
-                 threads=0):
+                 threads=0, ctx=None):
         self.n = n_streams
         self.parsers = [frontend.Parser(decoder_options) for _ in range(n_streams)]
-        self.ctx = Context(device, n_streams, max_width, max_height)
+        self.ctx = ctx if ctx is not None else Context(device, n_streams, max_width, max_height)
         self.threads = threads
 
     def parse_step(self, packets, stream_ids=None):
@@ -246,8 +246,30 @@ class BatchDecoder:
         parsers = [self.parsers[int(s)] for s in ids]
         return frontend.parse_step(parsers, packets, ids, self.threads)
 
-    def decode_step(self, packets, out_flags=_lib.OUT_RGBA, stream_ids=None):
-        pics, mbs, events, errs, pic_of = self.parse_step(packets, stream_ids)
-        if len(pics):
-            self.ctx.submit_step(pics, mbs, events, out_flags)
-        return errs
+    def decode_step(self, packets, out_flags=_lib.OUT_RGBA, stream_ids=None, host_rgba=None, rgba_stride=0):
+        """One decode_next_picture per stream through h263cu_decode_step: threaded parse into the
+        context's pinned staging, asynchronous upload + reconstruction (+ RGBA read-back into the
+        pinned buffer `host_rgba` when given).  Returns the per-picture error codes."""
+        plan = self.plan_step(packets, stream_ids)
+        return self.decode_planned(plan, out_flags, host_rgba, rgba_stride)
+
+    def plan_step(self, packets, stream_ids=None):
+        """The pointer arrays h263cu_decode_step takes, built once for a list of packets (bytes or
+        uint8 arrays, kept alive by the plan)."""
+        n = len(packets)
+        ids = np.arange(self.n, dtype=np.uint32)[:n] if stream_ids is None else np.ascontiguousarray(stream_ids, np.uint32)
+        bufs = [np.frombuffer(pk, np.uint8) if not isinstance(pk, np.ndarray) else pk for pk in packets]
+        return {
+            "n": n, "bufs": bufs, "ids": ids,
+            "parsers": (C.c_void_p * n)(*[self.parsers[int(s)].h for s in ids]),
+            "packets": (C.c_void_p * n)(*[b.ctypes.data for b in bufs]),
+            "lens": (C.c_size_t * n)(*[b.size for b in bufs]),
+            "errs": np.zeros(n, np.int32),
+        }
+
+    def decode_planned(self, plan, out_flags=_lib.OUT_RGBA, host_rgba=None, rgba_stride=0):
+        nd = C.c_uint32(0)
+        _lib.check(_lib.lib().h263cu_decode_step(
+            self.ctx.h, plan["parsers"], plan["packets"], plan["lens"], plan["ids"].ctypes.data, plan["n"], self.threads,
+            out_flags, host_rgba, rgba_stride, plan["errs"].ctypes.data, C.byref(nd)))
+        return plan["errs"]

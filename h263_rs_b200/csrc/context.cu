@@ -88,6 +88,15 @@ struct h263cu_ctx {
     h263cu_step ring[2];
     cudaEvent_t ring_h2d_done[2] = {}, ring_run_done[2] = {};
     int ring_pos = 0;
+    // pinned staging of h263cu_decode_step, one set per side-info ring slot (grow only)
+    struct Staging {
+        h263cu_pic* pics = nullptr;
+        h263cu_mb* mbs = nullptr;
+        h263cu_event* events = nullptr;
+        size_t pic_cap = 0, mb_cap = 0, ev_cap = 0;
+    } staging[2];
+    std::vector<int32_t> pic_of_input;
+    std::vector<uint64_t> rgba_offsets;
     // RGBA ring read-back tracking
     cudaEvent_t rgba_written[2] = {}, rgba_read[2] = {};
     // timing
@@ -290,6 +299,16 @@ int upload_into(h263cu_ctx* c, h263cu_step* s, const h263cu_pic* pics, uint32_t 
     return 0;
 }
 
+template <typename T>
+int grow_pinned(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr, *cap = 0;
+    const size_t n = need + need / 4 + 64;
+    CU_TRY(cudaHostAlloc((void**)p, n * sizeof(T), cudaHostAllocDefault));
+    *cap = n;
+    return 0;
+}
 void free_step_buffers(h263cu_step* s) {
     if (s->d_mbs) cudaFree(s->d_mbs);
     if (s->d_events) cudaFree(s->d_events);
@@ -402,6 +421,11 @@ void h263cu_destroy(h263cu_ctx* c) {
     if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
     if (c->s_pics) cudaStreamSynchronize(c->s_pics);
     for (int i = 0; i < 2; i++) free_step_buffers(&c->ring[i]);
+    for (auto& st : c->staging) {
+        if (st.pics) cudaFreeHost(st.pics);
+        if (st.mbs) cudaFreeHost(st.mbs);
+        if (st.events) cudaFreeHost(st.events);
+    }
     for (int i = 0; i < h263cu_ctx::PIC_RING; i++) {
         if (c->h_pics[i]) cudaFreeHost(c->h_pics[i]);
         if (c->d_pics[i]) cudaFree(c->d_pics[i]);
@@ -551,6 +575,41 @@ int h263cu_submit_step_readback(h263cu_ctx* c, const h263cu_pic* pics, uint32_t 
     }
     CU_TRY(cudaEventRecord(c->rgba_read[ring], c->s_d2h));
     return 0;
+}
+
+int h263cu_decode_step(h263cu_ctx* c, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                       const uint32_t* stream_ids, uint32_t n, int threads, uint32_t out_flags, uint8_t* host_rgba,
+                       uint64_t rgba_stride, int* per_pic_err, uint32_t* n_decoded) {
+    if (!c || !parsers || !packets || !lens) return H263CU_ERR_BAD_ARGUMENT;
+    if (n_decoded) *n_decoded = 0;
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    // capacities: a picture holds at most mbw * mbh macroblocks of this context; every event costs at least
+    // 3 bits of bitstream and takes at most 2 units
+    size_t bytes = 0;
+    for (uint32_t i = 0; i < n; i++) bytes += lens[i];
+    const size_t mb_need = (size_t)n * c->mbw * c->mbh, ev_need = bytes * 16 / 3 + 16 * (size_t)n;
+    if (mb_need > 0xFFFFFFFFull || ev_need > 0xFFFFFFFFull) return H263CU_ERR_CAPACITY;
+    const int slot = c->ring_pos;  // the ring slot submit_common is about to use
+    h263cu_ctx::Staging& st = c->staging[slot];
+    // the copy engine has finished with this staging set (it was read two submits ago)
+    CU_TRY(cudaEventSynchronize(c->ring_h2d_done[slot]));
+    int e;
+    if ((e = grow_pinned(&st.pics, &st.pic_cap, n)) || (e = grow_pinned(&st.mbs, &st.mb_cap, mb_need)) ||
+        (e = grow_pinned(&st.events, &st.ev_cap, ev_need)))
+        return e;
+    c->pic_of_input.resize(n);
+    uint32_t np = 0, nm = 0, nu = 0;
+    e = h263cu_parse_step(parsers, packets, lens, stream_ids, n, threads, st.pics, st.mbs, (uint32_t)st.mb_cap, st.events,
+                          (uint32_t)st.ev_cap, &np, &nm, &nu, per_pic_err, c->pic_of_input.data());
+    if (e) return e;
+    if (n_decoded) *n_decoded = np;
+    if (np == 0) return 0;
+    if (!host_rgba) return submit_common(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags);
+    c->rgba_offsets.resize(np);
+    for (uint32_t i = 0; i < n; i++)
+        if (c->pic_of_input[i] >= 0) c->rgba_offsets[(size_t)c->pic_of_input[i]] = (uint64_t)i * rgba_stride;
+    return h263cu_submit_step_readback(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags, host_rgba, c->rgba_offsets.data());
 }
 
 int h263cu_sync(h263cu_ctx* c) {

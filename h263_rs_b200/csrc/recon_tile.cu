@@ -57,11 +57,6 @@ constexpr int WARP_MBS = 4;      // macroblocks per warp
 #ifndef H263_L2_POLICY
 #define H263_L2_POLICY 0
 #endif
-// 1 = BT.601 through mad.wide: (y << 16) * 76309 + (term << 16) leaves (y * 76309 + term) >> 16 in the high
-// word, one instruction per channel instead of multiply-add + shift
-#ifndef H263_RGBA_WIDE
-#define H263_RGBA_WIDE 0
-#endif
 constexpr int CTA_WARPS = H263_CTA_WARPS;
 // Persistent warps drawing tiles from a global counter were measured SLOWER than one CTA per 32
 // consecutive macroblocks (325 vs 303 us per 1024-CIF step): neighbouring tiles then run on different
@@ -200,24 +195,6 @@ __device__ __forceinline__ CT chroma_terms_folded(int cb, int cr, int kr, int kg
 }
 __device__ __forceinline__ uint32_t rgba_px(int y, const CT& t) {
     const int r = (y * 76309 + t.r) >> 16, g = (y * 76309 + t.g) >> 16, b = (y * 76309 + t.b) >> 16;
-    return pack_sat(g, r, pack_sat(255, b, 0));
-}
-
-// The same through 64-bit multiply-adds: with y16 = y << 16 and the chroma terms held as term << 16,
-// y16 * 76309 + term64 = (y * 76309 + term) << 16 exactly, so the high word is the shifted channel.
-struct CT64 {
-    long long r, g, b;
-};
-__device__ __forceinline__ CT64 chroma_terms_wide(int cb16, int cr16, int kr, int kg, int kb) {
-    CT64 t;
-    t.r = (long long)cr16 * kr + ((long long)(32768 - 128 * 104597 - 16 * 76309) << 16);
-    t.g = (long long)cr16 * kg + ((long long)cb16 * -25675 + ((long long)(32768 + 128 * 53279 + 128 * 25675 - 16 * 76309) << 16));
-    t.b = (long long)cb16 * kb + ((long long)(32768 - 128 * 132201 - 16 * 76309) << 16);
-    return t;
-}
-__device__ __forceinline__ uint32_t rgba_px_wide(int y16, const CT64& t) {
-    const int r = (int)(((long long)y16 * 76309 + t.r) >> 32), g = (int)(((long long)y16 * 76309 + t.g) >> 32),
-              b = (int)(((long long)y16 * 76309 + t.b) >> 32);
     return pack_sat(g, r, pack_sat(255, b, 0));
 }
 
@@ -833,31 +810,6 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 uint8_t* o = pools.rgba + (size_t)ma.z * 16 + (size_t)(rg * 4) * rgba_pitch + (size_t)(h * 32);
                 const int kr = opaque(104597), kg = opaque(-53279), kb = opaque(132201);
 #pragma unroll
-#if H263_RGBA_WIDE
-#pragma unroll
-                for (int cr2 = 0; cr2 < 2; cr2++) {
-                    uint32_t px[2][8];
-#pragma unroll
-                    for (int half = 0; half < 2; half++) {  // pixels 0..3 use chroma samples 0, 1 (low lanes), 4..7 samples 2, 3
-                        const uint32_t cbe = ce[0][cr2], cre = ce[1][cr2], cbo = co[0][cr2], cro = co[1][cr2];
-                        const CT64 ta = half ? chroma_terms_wide((int)(cbe & 0xFFFF0000u), (int)(cre & 0xFFFF0000u), kr, kg, kb)
-                                             : chroma_terms_wide((int)(cbe << 16), (int)(cre << 16), kr, kg, kb);
-                        const CT64 tb = half ? chroma_terms_wide((int)(cbo & 0xFFFF0000u), (int)(cro & 0xFFFF0000u), kr, kg, kb)
-                                             : chroma_terms_wide((int)(cbo << 16), (int)(cro << 16), kr, kg, kb);
-#pragma unroll
-                        for (int rr = 0; rr < 2; rr++) {
-                            const RowSum& L = ly[cr2 * 2 + rr];
-                            const uint32_t le = half ? L.e1 : L.e0, lo = half ? L.o1 : L.o0;
-                            px[rr][half * 4 + 0] = rgba_px_wide((int)(le << 16), ta);
-                            px[rr][half * 4 + 1] = rgba_px_wide((int)(lo << 16), ta);
-                            px[rr][half * 4 + 2] = rgba_px_wide((int)(le & 0xFFFF0000u), tb);
-                            px[rr][half * 4 + 3] = rgba_px_wide((int)(lo & 0xFFFF0000u), tb);
-                        }
-                    }
-                    st_global_v8(o + (size_t)(cr2 * 2 + 0) * rgba_pitch, px[0]);
-                    st_global_v8(o + (size_t)(cr2 * 2 + 1) * rgba_pitch, px[1]);
-                }
-#else
 #pragma unroll
                 for (int cr2 = 0; cr2 < 2; cr2++) {
                     // chroma row cr2 serves luma rows 2*cr2, 2*cr2+1; sample j serves pixels 2j, 2j+1
@@ -880,7 +832,6 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                         st_global_v8(o + (size_t)(cr2 * 2 + rr) * rgba_pitch, px);
                     }
                 }
-#endif
             }
         }
     }

@@ -206,6 +206,19 @@ int h263cu_submit_step(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_pics, con
 int h263cu_submit_step_readback(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
                                 uint32_t n_mbs, const h263cu_event* events, uint32_t n_units,
                                 uint32_t out_flags, uint8_t* host_rgba, const uint64_t* rgba_offsets);
+/* Batched H263State::decode_next_picture (state.rs:138-489) from the bitstream: packet i is the next
+ * picture of parsers[i] / stream_ids[i] (NULL: stream i).  The serial VLC parse runs on `threads`
+ * host threads (h263cu_parse_step) into pinned staging owned by the context, the side info goes to
+ * the device through the double-buffered ring, and the step is reconstructed asynchronously -- the
+ * call returns as soon as the work is queued, so the parse of the next step overlaps this step's
+ * kernels and copies.  Pictures that fail to parse are reported in per_pic_err[i] (may be NULL),
+ * leave their stream untouched (the reference's transactional behaviour, state.rs:120-137) and are
+ * left out of the step; *n_decoded (may be NULL) counts the rest.  When host_rgba is not NULL the
+ * RGBA picture of input i is copied to host_rgba + i * rgba_stride (tight rows of 4 * width bytes)
+ * on the read-back stream; call h263cu_sync before reading it. */
+int h263cu_decode_step(h263cu_ctx*, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                       const uint32_t* stream_ids, uint32_t n, int threads, uint32_t out_flags, uint8_t* host_rgba,
+                       uint64_t rgba_stride, int* per_pic_err, uint32_t* n_decoded);
 int h263cu_sync(h263cu_ctx*);
 
 /* DecodedPicture accessors (h263/src/decoder/picture.rs:60-142): tight row-major planes,

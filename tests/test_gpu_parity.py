@@ -212,6 +212,56 @@ def test_readback_pipeline_matches():
         L.h263cu_free_pinned(bufs[t])
 
 
+def test_decode_step_from_bitstream_with_readback_and_bad_packet():
+    """h263cu_decode_step: bitstream packets in, RGBA in pinned host memory out, parse of step t+1
+    overlapping the device work of step t.  A packet that fails to parse is reported, leaves its
+    stream untouched (state.rs:120-137) and the stream carries on with the next good packet."""
+    import ctypes as C
+
+    n, t_steps = 5, 4
+    streams = [synth.make_stream(176, 144, t_steps, 700 + s, mv_mode=s % 3) for s in range(n)]
+    refs = [oracle_decode_stream(p) for p in streams]
+    dec = api.BatchDecoder(n, 176, 144, threads=3)
+    L = _lib.lib()
+    size = 176 * 144 * 4
+    bufs, errs_all = [], []
+    nxt = [0] * n  # next picture of every stream
+    sent = []
+    for t in range(t_steps + 1):
+        packets, which = [], []
+        for s in range(n):
+            if s == 2 and t == 1:
+                packets.append(b"\x12\x34\x56\x78\x9a")  # no picture start code
+                which.append(-1)
+            elif nxt[s] < t_steps:
+                packets.append(streams[s][nxt[s]])
+                which.append(nxt[s])
+                nxt[s] += 1
+            else:
+                packets.append(b"")  # stream has ended: empty packet fails to parse, nothing happens
+                which.append(-1)
+        host = L.h263cu_alloc_pinned(n * size)
+        assert host
+        bufs.append(host)
+        errs = dec.decode_step(packets, host_rgba=host, rgba_stride=size).copy()
+        errs_all.append(errs)
+        sent.append(which)
+    dec.ctx.sync()
+    for t in range(t_steps + 1):
+        arr = np.ctypeslib.as_array(C.cast(bufs[t], C.POINTER(C.c_uint8)), shape=(n * size,))
+        for s in range(n):
+            k = sent[t][s]
+            if k < 0:
+                assert errs_all[t][s] != 0, (t, s)
+                continue
+            assert errs_all[t][s] == 0, (t, s, int(errs_all[t][s]))
+            assert np.array_equal(arr[s * size : (s + 1) * size], refs[s][k]["rgba"]), (s, t)
+        L.h263cu_free_pinned(bufs[t])
+    for s in range(n):
+        y, cb, cr = dec.ctx.read_yuv(s)
+        assert np.array_equal(y, refs[s][-1]["y"]) and np.array_equal(cb, refs[s][-1]["cb"]) and np.array_equal(cr, refs[s][-1]["cr"])
+
+
 def test_device_errors_are_loud():
     ctx = api.Context(0, 2, 176, 144)
     pk = synth.make_stream(352, 288, 1, 1)
