@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("H263CU_LIB", os.path.join(HERE, "libh263cu.so"))
 
 OK = 0
+ERR_INVALID_BITSTREAM = -12
 ERR_UNHANDLED_IO_ERROR = -16
 ERR_BAD_ARGUMENT = -100
 ERR_CUDA = -101
@@ -72,7 +73,7 @@ SYMBOLS = [
     "h263cu_checksums", "h263cu_timer_start", "h263cu_timer_stop", "h263cu_launch_count",
     "h263cu_profile_enable", "h263cu_profile_read",
     "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength", "h263cu_synth_default_params",
-    "h263cu_synth_stream",
+    "h263cu_synth_stream", "h263cu_flv_scan", "h263cu_flv_mux",
 ]
 
 _lib = None
@@ -138,6 +139,10 @@ def lib():
     L.h263cu_synth_default_params.restype = None
     L.h263cu_synth_stream.restype = C.c_int64
     L.h263cu_synth_stream.argtypes = [C.POINTER(SynthParams), vp, C.c_size_t, vp, vp]
+    L.h263cu_flv_scan.restype = C.c_int64
+    L.h263cu_flv_scan.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.POINTER(u32)]
+    L.h263cu_flv_mux.restype = C.c_int64
+    L.h263cu_flv_mux.argtypes = [vp, vp, vp, vp, u32, u32, u32, vp, C.c_size_t]
     _lib = L
     return L
 

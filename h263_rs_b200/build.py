@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libh263cu.so")
-SOURCES = ["kernels.cu", "recon_tile.cu", "deblock_tile.cu", "context.cu", "frontend.cpp", "synth.cpp"]
+SOURCES = ["kernels.cu", "recon_tile.cu", "deblock_tile.cu", "context.cu", "frontend.cpp", "synth.cpp", "flv.cpp"]
 DEPS = SOURCES + ["kernels.cuh", "recon_common.cuh", "device_math.cuh", "bitio.hpp", "vlc_codes.inc", os.path.join("..", "..", "include", "h263cu.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 

@@ -257,6 +257,30 @@ int h263cu_deblock(const uint8_t* data, size_t len, size_t width, uint8_t streng
 /* deblock::deblock::QUANT_TO_STRENGTH (deblock/src/deblock.rs:5-8) */
 extern const uint8_t h263cu_quant_to_strength[32];
 
+/* ---- FLV container feed (the caller side of H263Reader::from_source(&packet[..]): one reader per FLV
+ *      video tag; Sorenson Spark is FLV video codec 2, one picture per tag) ------------------------- */
+typedef struct h263cu_flv_packet { /* 24 bytes */
+    uint64_t offset;       /* of the picture packet inside the FLV buffer (past the 1-byte video header) */
+    uint32_t size;         /* bytes of the picture packet */
+    uint32_t timestamp_ms; /* 32-bit tag timestamp (extended byte included) */
+    uint8_t frame_type;    /* 1 key, 2 inter, 3 disposable inter */
+    uint8_t codec_id;      /* always 2 (Sorenson H.263): other video codecs are skipped */
+    uint16_t reserved;
+    uint32_t reserved2;
+} h263cu_flv_packet;
+
+/* Zero-copy scan of an FLV byte stream: lists its H.263 video packets in file order.  Returns how many
+ * there are (fill up to `cap` of them; call with cap = 0 to count) or a negative error when the buffer
+ * is not FLV.  A buffer that ends inside a tag (streaming input) ends the scan at the last complete tag.
+ * Audio, script, other-codec and video-info tags are skipped and counted in *n_other_tags (may be NULL). */
+int64_t h263cu_flv_scan(const uint8_t* data, size_t len, h263cu_flv_packet* out, size_t cap, uint32_t* n_other_tags);
+/* The matching muxer for generated streams (tests, examples): wraps n picture packets (as laid out by
+ * h263cu_synth_stream) into an FLV byte stream, one video tag per picture at i * ms_per_picture;
+ * frame_types may be NULL (first = key, rest = inter); filler_every > 0 adds an audio and a script tag
+ * before every filler_every-th picture.  Returns the bytes needed / written, or a negative error. */
+int64_t h263cu_flv_mux(const uint8_t* packets, const uint64_t* pkt_off, const uint32_t* pkt_len, const uint8_t* frame_types,
+                       uint32_t n, uint32_t ms_per_picture, uint32_t filler_every, uint8_t* out, size_t cap);
+
 /* ---- synthetic Sorenson-flavour bitstream generator (the repo has no encoder) ---------- */
 typedef struct h263cu_synth_params {
     uint32_t width, height;
