@@ -435,15 +435,18 @@ def run_ours(args, rank, world, local_rank, dist):
     extras = {}
     if rank == 0 and world == 1:
         n_cpu = host_threads()
-        sample_steps = 1 + 2 + 4  # I + 2 warm + 4 timed
-        sample_streams = min(U, max(n_cpu * 4, 64))
+        # bounded sample: ~10-20 s of CPU work (one CIF picture costs the port ~1.5 ms of one core)
+        timed_steps = min(10, total - 3)
+        sample_steps = 1 + 2 + timed_steps  # I + 2 warm + timed
+        sample_streams = min(U, 768)
         secs = cpu_steps(blobs, range(sample_steps), n_cpu, sample_streams)
         tt = sum(s for s, _ in secs[3:])
         pp = sum(p for _, p in secs[3:])
         cpu_baseline = {
             "value": pp / tt / 1e6, "unit": UNIT, "cores": n_cpu, "kind": "port",
-            "sample": "4 timed steps x %d CIF streams of the same workload (full parse + recon + RGBA), %d host threads; "
-                      "C++ restatement of h263-rs, not the Rust build (no Rust toolchain)" % (sample_streams, n_cpu),
+            "sample": "%d timed steps x %d CIF streams of the same workload (full parse + recon + RGBA, %.1f s of CPU "
+                      "work), %d host threads; C++ restatement of h263-rs, not the Rust build (no Rust toolchain)"
+                      % (timed_steps, sample_streams, tt * n_cpu, n_cpu),
         }
         if not args.skip_extras:
             extras["single_stream_config2"] = single_stream(api, frontend, local_rank)
