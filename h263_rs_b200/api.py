@@ -95,6 +95,15 @@ class DecodedPicture:
     def as_chroma_r(self):
         return self._cr
 
+    def format(self):
+        """The picture's dimensions (DecodedPicture::format, picture.rs:60-66) as (width, height)."""
+        return self.width, self.height
+
+    def as_header(self):
+        """The header fields the reference keeps with a decoded picture (DecodedPicture::as_header)."""
+        return {"width": self.width, "height": self.height, "picture_type": self.picture_type,
+                "quantizer": self.quantizer, "temporal_reference": self.temporal_reference}
+
     def luma_samples_per_row(self):
         return self.width
 
@@ -223,6 +232,20 @@ class H263State:
         i = self.ctx.stream_info(0)
         y, cb, cr = self.ctx.read_yuv(0)
         return DecodedPicture(i["width"], i["height"], i["pic_type"], i["pquant"], i["tr"], y, cb, cr)
+
+    def get_reference_picture(self):
+        """state.rs:72-78.  The reference picture is the last non-disposable picture; disposable
+        pictures do not decode in the reference (macroblock.rs:461-465), so it is the last picture."""
+        return self.get_last_picture()
+
+    def parse_picture(self, packet):
+        """Header-only peek (H263State::parse_picture, state.rs:102-111): no decoder state changes."""
+        return frontend.peek_picture(bytes(packet), self.decoder_options)
+
+    def cleanup_buffers(self):
+        """state.rs:81-98 drops every picture except the last and the reference one.  The device context
+        never holds more than those two plane slots per stream, so there is nothing to free."""
+        return None
 
     def get_last_rgba(self):
         """RGBA of the last picture (fused yuv420_to_rgba, or deblock + yuv420_to_rgba)."""

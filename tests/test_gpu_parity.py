@@ -262,6 +262,26 @@ def test_decode_step_from_bitstream_with_readback_and_bad_packet():
         assert np.array_equal(y, refs[s][-1]["y"]) and np.array_equal(cb, refs[s][-1]["cb"]) and np.array_equal(cr, refs[s][-1]["cr"])
 
 
+def test_h263state_facade_surface():
+    """The rest of the reference's H263State / DecodedPicture surface (state.rs:53-111, picture.rs:60-142)."""
+    pk = synth.make_stream(176, 144, 3, 21)
+    st = api.H263State()
+    assert st.is_sorenson() and st.get_last_picture() is None and st.get_reference_picture() is None
+    hdr = st.parse_picture(pk[0])
+    assert (hdr["width"], hdr["height"], hdr["pic_type"]) == (176, 144, 0)
+    assert st.get_last_picture() is None  # the peek changes nothing
+    ref = oracle_decode_stream(pk)
+    for i, p in enumerate(pk):
+        st.decode_next_picture(p)
+        st.cleanup_buffers()
+        pic = st.get_last_picture()
+        assert pic.format() == (176, 144) and pic.luma_samples_per_row() == 176 and pic.chroma_samples_per_row() == 88
+        h = pic.as_header()
+        assert h["quantizer"] == ref[i]["info"]["quant"] and h["temporal_reference"] == ref[i]["info"]["tr"]
+        assert np.array_equal(pic.as_luma(), ref[i]["y"]) and np.array_equal(pic.as_chroma_b(), ref[i]["cb"])
+        assert np.array_equal(st.get_reference_picture().as_chroma_r(), ref[i]["cr"])
+
+
 def test_device_errors_are_loud():
     ctx = api.Context(0, 2, 176, 144)
     pk = synth.make_stream(352, 288, 1, 1)
