@@ -39,7 +39,8 @@ constexpr int WARP_MBS = 4;      // macroblocks per warp
 #define H263_LDG64 0
 #endif
 // Ablation builds for time attribution (results are wrong by design): 1 = no event walk / transform,
-// 2 = no prediction loads (every macroblock treated as intra), 4 = no RGBA, 8 = no plane stores.
+// 2 = no prediction loads (every macroblock treated as intra), 4 = no RGBA, 8 = no plane stores,
+// 16 = RGBA computed but not stored.
 #ifndef H263_ABLATE
 #define H263_ABLATE 0
 #endif
@@ -829,6 +830,10 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                         px[5] = rgba_px((int)(L.o1 & 0xFFFFu), t2);
                         px[6] = rgba_px((int)(L.e1 >> 16), t3);
                         px[7] = rgba_px((int)(L.o1 >> 16), t3);
+                        if (H263_ABLATE & 16) {  // RGBA computed, store suppressed (kept alive by an impossible condition)
+                            if ((px[0] ^ px[1] ^ px[2] ^ px[3] ^ px[4] ^ px[5] ^ px[6] ^ px[7]) == 0x12345678u)
+                                st_global_v8(o + (size_t)(cr2 * 2 + rr) * rgba_pitch, px);
+                        } else
                         st_global_v8(o + (size_t)(cr2 * 2 + rr) * rgba_pitch, px);
                     }
                 }
