@@ -23,13 +23,13 @@ namespace h263fe {
 void VlcTable::build(const VlcCode* codes, int n) {
     max_len = 0;
     for (int i = 0; i < n; i++) max_len = std::max(max_len, codes[i].len);
-    lut.assign((size_t)1 << max_len, VlcEntry{0, 2, 0, 0, 0});
+    lut.assign((size_t)1 << max_len, VlcEntry{(uint8_t)(2u << 5), 0, 0, 0});
     for (int i = 0; i < n; i++) {
         uint32_t v = 0;
         for (int k = 0; k < codes[i].len; k++) v = (v << 1) | (uint32_t)(codes[i].bits[k] - '0');
         int rest = max_len - codes[i].len;
-        VlcEntry e{(uint8_t)codes[i].len, (uint8_t)codes[i].kind, (int8_t)codes[i].a, (uint8_t)codes[i].b,
-                   (uint8_t)codes[i].c};
+        VlcEntry e{(uint8_t)((unsigned)codes[i].len | ((unsigned)codes[i].kind << 5)), (int8_t)codes[i].a,
+                   (uint8_t)codes[i].b, (uint8_t)codes[i].c};
         for (uint32_t s = 0; s < (1u << rest); s++) lut[((size_t)v << rest) | s] = e;
     }
 }
@@ -87,23 +87,23 @@ static bool std_dims(int kind, uint16_t* w, uint16_t* h) {
 // Start code search (reader.rs:240-258): 17 bits 0...01, preceded by stuffing that may not
 // exceed the distance to the next byte boundary (plus the reference's off-by-one).
 static int find_start_code(BitReader& r, uint32_t* skipped) {
-    size_t save = r.pos;
-    uint32_t max_skip = (uint32_t)((8 - (r.pos & 7)) & 7);
+    const size_t save = r.pos();
+    uint32_t max_skip = (uint32_t)((8 - (r.pos() & 7)) & 7);
     uint32_t skip = 0;
     for (;;) {
         if (r.avail() < 17) {
-            r.pos = save;
+            r.seek(save);
             return H263CU_ERR_UNHANDLED_IO_ERROR;
         }
         if (r.peek_padded(17) == 1) break;
         if (skip > max_skip) {
-            r.pos = save;
+            r.seek(save);
             return H263CU_ERR_MIDDLE_OF_BITSTREAM;
         }
-        r.pos += 1;
+        r.consume(1);
         skip += 1;
     }
-    r.pos = save;
+    r.seek(save);
     *skipped = skip;
     return 0;
 }
@@ -258,9 +258,13 @@ struct PendingState {
 
 // One block (block.rs:670-755).  Events go to ev_run/ev_level; returns 0 or an error.
 // *overflow is set when the run lengths push the zig-zag index past 63 (rle.rs:125-127).
-static inline int parse_block(BitReader& r, const Header& hd, uint32_t options, bool intra, bool coded, int* dc_code,
-                              uint8_t* ev_run, int16_t* ev_level, int* nev, bool* overflow) {
+static inline int parse_block(BitReader& r_io, const Header& hd, uint32_t options, bool intra, bool coded, int* dc_code,
+                              uint8_t* __restrict ev_run, int16_t* __restrict ev_level, int* nev, bool* overflow) {
     const VlcTable& T = vlc_table(T_TCOEF);
+    // The reader works on a private copy whose address never escapes: the byte stores into ev_run / the records
+    // may alias anything the compiler cannot prove local, and would otherwise force the bit window through memory
+    // on every event.
+    BitReader r = r_io;
     uint32_t v;
     *dc_code = -1;
     *nev = 0;
@@ -270,18 +274,22 @@ static inline int parse_block(BitReader& r, const Header& hd, uint32_t options, 
         if (v == 0 || v == 128) return H263CU_ERR_INVALID_INTRA_DC;
         *dc_code = (int)v;
     }
-    if (!coded) return 0;
+    if (!coded) {
+        r_io = r;
+        return 0;
+    }
     const bool sorenson_v1 = (options & H263CU_OPT_SORENSON_SPARK_BITSTREAM) && hd.version == 1;
     int idx = intra ? 1 : 0;
     int n = 0;
+    bool ovf = false;
     for (;;) {
         const VlcEntry* e;
-        if (!r.read_vlc(T, &e)) return H263CU_ERR_UNHANDLED_IO_ERROR;
+        bool eof_sign;
+        if (!r.read_vlc_bits(T, 1, &e, &v, &eof_sign)) return H263CU_ERR_UNHANDLED_IO_ERROR;  // code + sign bit from one window
         int last, run, level;
-        if (e->kind == 0) {
-            if (!r.read(1, &v)) return H263CU_ERR_UNHANDLED_IO_ERROR;
+        if (e->kind() == 0) {
             last = e->a, run = e->b, level = v ? -(int)e->c : (int)e->c;
-        } else if (e->kind == 3) {
+        } else if (e->kind() == 3) {
             unsigned width = 8;
             if (sorenson_v1) {
                 if (!r.read(1, &v)) return H263CU_ERR_UNHANDLED_IO_ERROR;
@@ -296,8 +304,8 @@ static inline int parse_block(BitReader& r, const Header& hd, uint32_t options, 
             return H263CU_ERR_INVALID_SHORT_COEFFICIENT;
         }
         idx += run;
-        if (idx >= 64) *overflow = true;
-        if (!*overflow) {
+        ovf |= idx >= 64;
+        if (!ovf) {
             ev_run[n] = (uint8_t)run;
             ev_level[n] = (int16_t)level;
             n++;
@@ -305,7 +313,9 @@ static inline int parse_block(BitReader& r, const Header& hd, uint32_t options, 
         idx += 1;
         if (last) break;
     }
-    *nev = *overflow ? 0 : n;
+    *overflow = ovf;
+    *nev = ovf ? 0 : n;
+    r_io = r;
     return 0;
 }
 
@@ -342,7 +352,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
     int16_t ev_level[6][64];
 
     for (;;) {
-        const size_t mb_start = r.pos;
+        const size_t mb_start = r.pos();
         uint32_t v;
         int err = 0;
         bool uncoded = false, stuffing = false;
@@ -376,11 +386,11 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                 err = H263CU_ERR_UNHANDLED_IO_ERROR;
                 break;
             }
-            if (en->kind == 1) {
+            if (en->kind() == 1) {
                 stuffing = true;
                 break;
             }
-            if (en->kind != 0) {
+            if (en->kind() != 0) {
                 err = H263CU_ERR_INVALID_MACROBLOCK_HEADER;
                 break;
             }
@@ -390,7 +400,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                 err = H263CU_ERR_UNHANDLED_IO_ERROR;
                 break;
             }
-            if (en->kind != 0) {
+            if (en->kind() != 0) {
                 err = H263CU_ERR_INVALID_MACROBLOCK_CODED_BITS;
                 break;
             }
@@ -413,7 +423,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                             err = H263CU_ERR_UNHANDLED_IO_ERROR;
                             break;
                         }
-                        if (en->kind != 0) {
+                        if (en->kind() != 0) {
                             err = H263CU_ERR_INVALID_MVD;
                             break;
                         }
@@ -424,7 +434,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
         } while (0);
 
         if (err) {
-            r.pos = mb_start;  // decode_macroblock is a transaction
+            r.seek(mb_start);  // decode_macroblock is a transaction
             if (err == H263CU_ERR_UNHANDLED_IO_ERROR) break;  // EOF ends the picture (state.rs:411)
             if ((err == H263CU_ERR_INVALID_MACROBLOCK_HEADER || err == H263CU_ERR_INVALID_MACROBLOCK_CODED_BITS) &&
                 !is_sorenson) {
@@ -434,10 +444,10 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                 if (ge == H263CU_ERR_MIDDLE_OF_BITSTREAM) break;  // InvalidGobHeader ends the picture
                 if (ge) break;                                    // EOF ends the picture
                 if (r.avail() < 17 + skipped + 5) break;          // EOF while reading the GOB number
-                size_t save = r.pos;
-                r.pos += 17 + skipped;
+                const size_t save = r.pos();
+                r.seek(save + 17 + skipped);
                 uint32_t gn = r.peek_padded(5);
-                r.pos = save;
+                r.seek(save);
                 if (gn == 0 || gn == 15) break;  // picture start / EOS: end of this picture
                 return H263CU_ERR_UNIMPLEMENTED_DECODING;
             }
