@@ -70,7 +70,7 @@ SYMBOLS = [
     "h263cu_create", "h263cu_destroy", "h263cu_device_of", "h263cu_alloc_pinned", "h263cu_free_pinned",
     "h263cu_step_upload", "h263cu_step_free", "h263cu_step_run", "h263cu_submit_step",
     "h263cu_submit_step_readback", "h263cu_decode_step", "h263cu_sync", "h263cu_stream_info", "h263cu_read_yuv", "h263cu_read_rgba",
-    "h263cu_checksums", "h263cu_timer_start", "h263cu_timer_stop", "h263cu_launch_count",
+    "h263cu_checksums", "h263cu_timer_start", "h263cu_timer_stop", "h263cu_launch_count", "h263cu_tiled_launch_count",
     "h263cu_profile_enable", "h263cu_profile_read",
     "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength", "h263cu_synth_default_params",
     "h263cu_synth_stream", "h263cu_flv_scan", "h263cu_flv_mux",
@@ -131,6 +131,8 @@ def lib():
         L.h263cu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
         L.h263cu_launch_count.restype = u64
         L.h263cu_launch_count.argtypes = [vp]
+        L.h263cu_tiled_launch_count.restype = u64
+        L.h263cu_tiled_launch_count.argtypes = [vp]
         L.h263cu_profile_enable.argtypes = [vp, i32]
         L.h263cu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
         L.h263cu_yuv420_to_rgba.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, vp]

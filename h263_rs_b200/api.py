@@ -189,6 +189,9 @@ class Context:
     def launch_count(self):
         return int(self.L.h263cu_launch_count(self.h))
 
+    def tiled_launch_count(self):
+        return int(self.L.h263cu_tiled_launch_count(self.h))
+
     def profile_enable(self, on=True):
         check(self.L.h263cu_profile_enable(self.h, int(on)))
 

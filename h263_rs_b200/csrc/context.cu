@@ -101,7 +101,7 @@ struct h263cu_ctx {
     cudaEvent_t rgba_written[2] = {}, rgba_read[2] = {};
     // timing
     cudaEvent_t t0 = nullptr, t1 = nullptr;
-    uint64_t launches = 0;
+    uint64_t launches = 0, tiled_launches = 0;
     // optional per-kernel timing (h263cu_profile_*): event pairs, kind 0 = recon, 1 = deblock
     bool profiling = false;
     std::vector<cudaEvent_t> prof_free;
@@ -209,8 +209,9 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         }
         max_w = std::max<uint32_t>(max_w, p.width);
         max_h = std::max<uint32_t>(max_h, p.height);
-        // the tiled kernel needs MB-aligned pictures and references with a replicated border
-        if ((p.width | p.height) & 15) tiled = false, aligned16 = false;
+        // the tiled kernel needs references with a replicated border; sizes that are not multiples of 16 take its
+        // edge fix-up instantiation, and the register-resident deblock kernel needs aligned pictures
+        if ((p.width | p.height) & 15) aligned16 = false;
         if ((p.flags & H263CU_PICFLAG_HAS_INTER) && !st.padded) tiled = false;
     }
     if (c->force_kernel == 1) tiled = false;
@@ -265,8 +266,10 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     cudaEvent_t pa = nullptr, pb = nullptr;
     if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
     const Pools pools{c->y_pool, c->cb_pool, c->cr_pool, c->rgba_pool, c->d_work_counter, c->pitch_y, c->pitch_c, c->rgba_pitch};
-    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? 1 : 0, pools, c->s_main);
+    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? (aligned16 ? 1 : 2) : 0, pools,
+                 c->s_main);
     c->launches++;
+    if (tiled) c->tiled_launches++;
     if (c->profiling) prof_end(c, pa, pb, 0);
     if (want_deblock) {
         if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
@@ -714,6 +717,7 @@ int h263cu_timer_stop(h263cu_ctx* c, float* ms) {
     return 0;
 }
 uint64_t h263cu_launch_count(h263cu_ctx* c) { return c ? c->launches : 0; }
+uint64_t h263cu_tiled_launch_count(h263cu_ctx* c) { return c ? c->tiled_launches : 0; }
 
 int h263cu_profile_enable(h263cu_ctx* c, int enable) {
     if (!c) return H263CU_ERR_BAD_ARGUMENT;

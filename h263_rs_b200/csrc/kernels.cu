@@ -291,7 +291,7 @@ void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* 
                   int tiled, const Pools& pools, cudaStream_t stream) {
     if (n_mbs == 0) return;
     if (tiled) {
-        launch_recon_tile(pics, mbs, events, n_mbs, emit_rgba, pools, stream);
+        launch_recon_tile(pics, mbs, events, n_mbs, emit_rgba, tiled == 2, pools, stream);
     } else {
         const uint32_t grid = (n_mbs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         recon_mb_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba);

@@ -42,13 +42,14 @@ struct Pools {
 
 // Fused reconstruction of every macroblock of a step: inverse RLE + dequant + classify +
 // IDCT + motion compensation + add/clamp -> planes, and BT.601 RGBA when `emit_rgba`.
-// tiled != 0 selects recon_tile_kernel (picture sizes multiple of 16, padded reference planes),
-// else the generic warp-per-macroblock recon_mb_kernel.
+// tiled != 0 selects recon_tile_kernel (padded reference planes), else the generic warp-per-macroblock
+// recon_mb_kernel.
+// tiled: 1 = every picture is a multiple of 16 in size, 2 = some are not (edge fix-up instantiation).
 void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
                   int emit_rgba, int tiled, const Pools& pools, cudaStream_t stream);
 // recon_tile.cu
 void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
-                       int emit_rgba, const Pools& pools, cudaStream_t stream);
+                       int emit_rgba, int unaligned, const Pools& pools, cudaStream_t stream);
 
 // Plane padding (bytes / rows) reserved around every reconstruction plane: the tiled kernel
 // replicates 16 luma / 8 chroma border pixels into it; the extra columns keep the interior

@@ -220,7 +220,11 @@ __device__ __forceinline__ uint32_t splat_hi(uint32_t w) { return __byte_perm(w,
 // PY / PC / PR: luma, chroma and RGBA row pitches in bytes when they are known at compile time (the
 // standard picture formats; all planes of a context share them), 0 = read them from the descriptors.
 // Constant pitches turn every row address of the epilogue into an immediate offset.
-template <int PY, int PC, int PR>
+// EDGE: pictures whose size is not a multiple of 16.  The planes are macroblock-rounded; the part of the last
+// macroblock column / row that lies outside the picture is overwritten with the picture's edge pixels before the
+// stores (and the border replication continues from there), so that prediction reads beyond the true edge see
+// read_sample's clamp (gather.rs:16-31).  Compiled out of the instantiations for aligned pictures.
+template <int PY, int PC, int PR, bool EDGE>
 __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
     recon_tile_kernel(const PicDev* __restrict__ pics, const h263cu_mb* __restrict__ mbs,
                       const h263cu_event* __restrict__ events, uint32_t n_mbs, int emit_rgba, const Pools pools) {
@@ -311,7 +315,12 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             W.bf[lane] = bflags;
             if (bb == 0) {
                 const int pitch_y = PY ? PY : P.pitch_y, pitch_c = PC ? PC : P.pitch_c;
-                const int mbw = P.w >> 4, mbh = P.h >> 4;
+                const int mbw = (P.w + 15) >> 4, mbh = (P.h + 15) >> 4;
+                // valid luma columns / rows of the last macroblock column / row (0 = all 16) and the same for
+                // chroma (0 = all 8)
+                const uint32_t ed = EDGE ? ((uint32_t)(P.w & 15) | ((uint32_t)(P.h & 15) << 4) | ((uint32_t)(P.cw & 7) << 8) |
+                                            ((uint32_t)(P.ch & 7) << 12))
+                                         : 0u;
                 const uint32_t rgba_pitch = PR ? PR : P.rgba_pitch;
                 uint32_t flags = inter ? MBF_INTER : 0u;
                 if (mbx == 0) flags |= MBF_LEFT;
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     make_uint4(P.cur_y4 + (uint32_t)((mby * 16 * pitch_y + mbx * 16) >> 2),
                                P.cur_c4 + (uint32_t)((mby * 8 * pitch_c + mbx * 8) >> 2),
                                P.rgba16 + (uint32_t)(mby * 16) * (rgba_pitch >> 4) + (uint32_t)(mbx * 4), flags);
-                *reinterpret_cast<uint4*>(&W.mb[bm][4]) = make_uint4((uint32_t)pitch_y | ((uint32_t)pitch_c << 16), rgba_pitch, pic, 0u);
+                *reinterpret_cast<uint4*>(&W.mb[bm][4]) = make_uint4((uint32_t)pitch_y | ((uint32_t)pitch_c << 16), rgba_pitch, pic, ed);
             }
         }
 
@@ -731,6 +740,62 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             cw[r][0] = __byte_perm(cy[r].e0, cy[r].o0, 0x6240);
             cw[r][1] = __byte_perm(cy[r].e1, cy[r].o1, 0x6240);
         }
+        if constexpr (EDGE) {
+            // keep `lo` bytes of a, take the rest from b (lo = 0..4)
+            auto merge = [](uint32_t a, uint32_t b, int lo) {
+                const uint32_t m = lo >= 4 ? 0xFFFFFFFFu : ((1u << (8 * lo)) - 1u);
+                return (a & m) | (b & ~m);
+            };
+            const uint32_t ed = mv.w;
+            const int vw = (int)(ed & 15u), vh = (int)((ed >> 4) & 15u), cvw = (int)((ed >> 8) & 7u), cvh = (int)((ed >> 12) & 7u);
+            const bool fix_r = (flags & MBF_RIGHT) != 0, fix_b = (flags & MBF_BOTTOM) != 0;
+            // right edge, luma: the pixel of column vw - 1 lives in the lane with h = (vw - 1) >> 3 of this row group
+            {
+                const int e = (vw - 1) & 15, keep = min(max(vw - 8 * h, 0), 8);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t mine = __byte_perm(yw[r][0], yw[r][1], (uint32_t)(e & 7)) & 0xFFu;
+                    const uint32_t other = __shfl_xor_sync(FULL, mine, 1);
+                    if (fix_r && vw) {
+                        const uint32_t sp = splat_lo((e >> 3) == h ? mine : other);
+                        yw[r][0] = merge(yw[r][0], sp, min(keep, 4));
+                        yw[r][1] = merge(yw[r][1], sp, max(keep - 4, 0));
+                    }
+                }
+            }
+            // right edge, chroma: every lane holds all 8 columns of its plane
+            if (fix_r && cvw) {
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const uint32_t sp = splat_lo(__byte_perm(cw[r][0], cw[r][1], (uint32_t)(cvw - 1)));
+                    cw[r][0] = merge(cw[r][0], sp, min(cvw, 4));
+                    cw[r][1] = merge(cw[r][1], sp, max(cvw - 4, 0));
+                }
+            }
+            // bottom edge: rows below row vh - 1 (chroma cvh - 1) repeat it; its owner is the lane of the same
+            // macroblock and h with rg = (vh - 1) >> 2 (chroma (cvh - 1) >> 1)
+            {
+                const int f = (vh - 1) & 15, rf = f & 3;
+                const uint32_t own0 = rf == 0 ? yw[0][0] : (rf == 1 ? yw[1][0] : (rf == 2 ? yw[2][0] : yw[3][0]));
+                const uint32_t own1 = rf == 0 ? yw[0][1] : (rf == 1 ? yw[1][1] : (rf == 2 ? yw[2][1] : yw[3][1]));
+                const int src = (lane & ~6) | ((f >> 2) << 1);
+                const uint32_t s0 = __shfl_sync(FULL, own0, src), s1 = __shfl_sync(FULL, own1, src);
+                if (fix_b && vh) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (rg * 4 + r > f) yw[r][0] = s0, yw[r][1] = s1;
+                }
+                const int cf = (cvh - 1) & 7;
+                const uint32_t c0 = (cf & 1) ? cw[1][0] : cw[0][0], c1 = (cf & 1) ? cw[1][1] : cw[0][1];
+                const int csrc = (lane & ~6) | ((cf >> 1) << 1);
+                const uint32_t t0 = __shfl_sync(FULL, c0, csrc), t1 = __shfl_sync(FULL, c1, csrc);
+                if (fix_b && cvh) {
+#pragma unroll
+                    for (int r = 0; r < 2; r++)
+                        if (rg * 2 + r > cf) cw[r][0] = t0, cw[r][1] = t1;
+                }
+            }
+        }
         if (unit_ok && !(H263_ABLATE & 8)) {
             uint8_t* py = pools.y + (size_t)(ma.x + (uint32_t)(rg * 4) * pitch_y4 + (uint32_t)(h * 2)) * 4;
             uint8_t* pc = (h ? pools.cr : pools.cb) + (size_t)(ma.y + (uint32_t)(rg * 2) * pitch_c4) * 4;
@@ -845,7 +910,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
 }
 
 void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs, int emit_rgba,
-                       const Pools& pools, cudaStream_t stream) {
+                       int unaligned, const Pools& pools, cudaStream_t stream) {
     if (n_mbs == 0) return;
     const uint32_t per_cta = CTA_WARPS * WARP_MBS;
     uint32_t grid = (n_mbs + per_cta * kTilesPerWarp - 1) / (per_cta * kTilesPerWarp);
@@ -860,14 +925,16 @@ void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_ev
     }
     // pitches of the standard formats (context.cu: pitch_y = 16*mbw + 64, pitch_c = round_up(8*mbw + 32, 16))
     const uint32_t py = pools.pitch_y, pc = pools.pitch_c, pr = pools.rgba_pitch;
-    if (py == 416 && pc == 208 && pr == 1408)  // CIF 352x288
-        recon_tile_kernel<416, 208, 1408><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+    if (unaligned)  // some picture of the step is not a multiple of 16 in size: edge fix-up, run-time pitches
+        recon_tile_kernel<0, 0, 0, true><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+    else if (py == 416 && pc == 208 && pr == 1408)  // CIF 352x288
+        recon_tile_kernel<416, 208, 1408, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
     else if (py == 240 && pc == 128 && pr == 704)  // QCIF 176x144
-        recon_tile_kernel<240, 128, 704><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+        recon_tile_kernel<240, 128, 704, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
     else if (py == 768 && pc == 384 && pr == 2816)  // 4CIF 704x576
-        recon_tile_kernel<768, 384, 2816><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+        recon_tile_kernel<768, 384, 2816, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
     else
-        recon_tile_kernel<0, 0, 0><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+        recon_tile_kernel<0, 0, 0, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
 }
 
 }  // namespace h263dev

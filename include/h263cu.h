@@ -240,6 +240,9 @@ int h263cu_timer_start(h263cu_ctx*);
 int h263cu_timer_stop(h263cu_ctx*, float* milliseconds);
 /* Number of kernel launches issued by this context so far. */
 uint64_t h263cu_launch_count(h263cu_ctx*);
+/* How many of the reconstruction launches took the tiled kernel (the fast path: references with a
+ * replicated border; any picture size) rather than the generic warp-per-macroblock kernel. */
+uint64_t h263cu_tiled_launch_count(h263cu_ctx*);
 /* Per-kernel timing: when enabled, every recon / deblock launch is bracketed by CUDA events
  * on the launching stream.  h263cu_profile_read synchronises, accumulates the elapsed times
  * since the last read into ms[0] (recon) / ms[1] (deblock+rgba) and the launch counts into

@@ -75,6 +75,13 @@ STREAMS = [
     dict(id="sqcif_many_events", w=128, h=96, n=4, seed=9, mean_events_x10=200, pct_cbp_inter=90),
     dict(id="tiny_24x40", w=24, h=40, n=5, seed=10, mv_mode=1),
     dict(id="qcif_all_intra_dense", w=176, h=144, n=3, seed=11, intra_period=1, pct_cbp_intra=100, mean_events_x10=120),
+    # sizes that are not multiples of 16 (the tiled kernel's edge fix-up): odd sizes, a single partial macroblock,
+    # partial columns / rows of 1 and 15 pixels, vectors pointing across the partial edge
+    dict(id="unaligned_161x99_odd", w=161, h=99, n=6, seed=12, mv_mode=2, pct_fourmv=20),
+    dict(id="unaligned_15x15", w=15, h=15, n=5, seed=13, mv_mode=1),
+    dict(id="unaligned_17x33", w=17, h=33, n=5, seed=14, mv_mode=2),
+    dict(id="unaligned_480x360", w=480, h=360, n=4, seed=15, mv_mode=2, intra_period=3),
+    dict(id="unaligned_47x31", w=47, h=31, n=6, seed=16, mv_mode=1, pct_intra=30),
 ]
 
 
@@ -114,6 +121,9 @@ def test_decode_next_picture_bit_exact(case):
         assert np.array_equal(cb, ref[i]["cb"]), (case["id"], i, "Cb")
         assert np.array_equal(cr, ref[i]["cr"]), (case["id"], i, "Cr")
         assert np.array_equal(st.get_last_rgba(), ref[i]["rgba"]), (case["id"], i, "RGBA")
+    # every picture took the tiled kernel, whatever its size (the generic kernel is only the A/B partner)
+    if st.ctx is not None:
+        assert st.ctx.tiled_launch_count() == sum(1 for r in ref if not isinstance(r, int)), case["id"]
 
 
 @pytest.mark.parametrize("case", [STREAMS[0], STREAMS[2], STREAMS[6], STREAMS[7]] + SMALL_ALIGNED, ids=lambda c: c["id"])
@@ -295,9 +305,8 @@ def test_device_errors_are_loud():
 
 
 def test_tiled_and_generic_kernels_agree_and_interleave(monkeypatch):
-    """The tiled kernel (MB-aligned sizes, padded references) and the generic warp-per-MB
-    kernel are two independent implementations: both must match the oracle, also when a
-    stream flips between them (aligned stream sharing steps with an unaligned one)."""
+    """The tiled kernel and the generic warp-per-MB kernel are two independent implementations: both
+    must match the oracle, on an aligned and an unaligned stream sharing steps, whichever is forced."""
     n = 8
     a = synth.make_stream(352, 288, n, 77, mv_mode=2, intra_period=4, pct_fourmv=20)
     b = synth.make_stream(200, 100, n, 78, mv_mode=1)
@@ -311,7 +320,7 @@ def test_tiled_and_generic_kernels_agree_and_interleave(monkeypatch):
         pa, pb = frontend.Parser(1), frontend.Parser(1)
         tb = 0
         for t in range(n):
-            with_b = t in (0, 1, 5) and force != "tile"
+            with_b = t in (0, 1, 5)
             parsers, packets, ids = [pa], [a[t]], [0]
             if with_b:
                 parsers, packets, ids = [pa, pb], [a[t], b[tb]], [0, 1]
