@@ -40,7 +40,8 @@ constexpr int WARP_MBS = 4;      // macroblocks per warp
 #endif
 // Ablation builds for time attribution (results are wrong by design): 1 = no event walk / transform,
 // 2 = no prediction loads (every macroblock treated as intra), 4 = no RGBA, 8 = no plane stores,
-// 16 = RGBA computed but not stored.
+// 16 = RGBA computed but not stored, 32 = Cr predicted from the Cb plane (chroma load sectors halved),
+// 64 = Cr stored onto the Cb plane (chroma store sectors halved).
 #ifndef H263_ABLATE
 #define H263_ABLATE 0
 #endif
@@ -136,13 +137,20 @@ __device__ __forceinline__ int round_q(float q, float m) { return __float2int_rz
 // The three aligned words that hold the 9 bytes a prediction row needs, p = word of the first pixel.
 // With H263_LDG64 they come from two 8-byte loads of the enclosing 16-byte window (two requests
 // instead of three on the L1 data pipe, the busiest unit of this kernel); odd = p is an odd word.
-__device__ __forceinline__ void load_row3(const uint32_t* p, bool odd, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+// `third` = the row needs its third word (it does unless the block starts word-aligned with a full-pel x vector);
+// `row` = the row is needed at all (the extra row below a unit only when the vector is half-pel in y).  A load pass
+// costs the L1 one look-up per distinct sector it touches, so lanes that do not need a word stay out of the pass.
+__device__ __forceinline__ void load_row3(const uint32_t* p, bool odd, bool third, bool row, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
 #if H263_LDG64
     const uint2* q = reinterpret_cast<const uint2*>(p - (odd ? 1 : 0));
     const uint2 v0 = __ldg(q), v1 = __ldg(q + 1);
     w0 = odd ? v0.y : v0.x, w1 = odd ? v1.x : v0.y, w2 = odd ? v1.y : v1.x;
 #else
-    w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    w0 = w1 = w2 = 0u;
+    if (row) {
+        w0 = __ldg(p), w1 = __ldg(p + 1);
+        if (third) w2 = __ldg(p + 2);
+    }
 #endif
 }
 
@@ -604,11 +612,10 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 RowSum hs[5];
 #pragma unroll
                 for (int r = 0; r < 5; r++) {
-                    // the fifth row is only needed for vertical interpolation; without it the load
-                    // repeats row 3 (an L1 hit) and its weight is 0
-                    const uint32_t* p = src + (r < 4 ? (uint32_t)r : 3u + wb) * pitch_y4;
+                    // the fifth row is only needed for vertical interpolation (its weight is 0 otherwise)
+                    const uint32_t* p = src + (uint32_t)r * pitch_y4;
                     uint32_t w0, w1, w2;
-                    load_row3(p, odd, w0, w1, w2);
+                    load_row3(p, odd, (fl & 7u) != 0, r < 4 || wb != 0, w0, w1, w2);
                     hs[r] = row_sum8(w0, w1, w2, sh, shb);
                 }
 #pragma unroll
@@ -639,13 +646,13 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 // chroma rows 2*rg, 2*rg+1 of the macroblock, all 8 columns, plane h
                 const uint32_t so = W.bd[bc];
                 const bool odd = (so & 1u) != 0;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(h ? pools.cr : pools.cb) + so + (uint32_t)(rg * 2) * pitch_c4;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>((H263_ABLATE & 32) ? pools.cb : (h ? pools.cr : pools.cb)) + so + (uint32_t)(rg * 2) * pitch_c4;
                 RowSum hs[3];
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
-                    const uint32_t* p = src + (r < 2 ? (uint32_t)r : 1u + wb) * pitch_c4;
+                    const uint32_t* p = src + (uint32_t)r * pitch_c4;
                     uint32_t w0, w1, w2;
-                    load_row3(p, odd, w0, w1, w2);
+                    load_row3(p, odd, (fc & 7u) != 0, r < 2 || wb != 0, w0, w1, w2);
                     hs[r] = row_sum8(w0, w1, w2, sh, shb);
                 }
 #pragma unroll
@@ -798,7 +805,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         }
         if (unit_ok && !(H263_ABLATE & 8)) {
             uint8_t* py = pools.y + (size_t)(ma.x + (uint32_t)(rg * 4) * pitch_y4 + (uint32_t)(h * 2)) * 4;
-            uint8_t* pc = (h ? pools.cr : pools.cb) + (size_t)(ma.y + (uint32_t)(rg * 2) * pitch_c4) * 4;
+            uint8_t* pc = ((H263_ABLATE & 64) ? pools.cb : (h ? pools.cr : pools.cb)) + (size_t)(ma.y + (uint32_t)(rg * 2) * pitch_c4) * 4;
 #pragma unroll
             for (int r = 0; r < 4; r++) *reinterpret_cast<uint2*>(py + r * pitch_y) = make_uint2(yw[r][0], yw[r][1]);
 #pragma unroll
