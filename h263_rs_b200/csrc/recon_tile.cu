@@ -41,7 +41,8 @@ constexpr int WARP_MBS = 4;      // macroblocks per warp
 // Ablation builds for time attribution (results are wrong by design): 1 = no event walk / transform,
 // 2 = no prediction loads (every macroblock treated as intra), 4 = no RGBA, 8 = no plane stores,
 // 16 = RGBA computed but not stored, 32 = Cr predicted from the Cb plane (chroma load sectors halved),
-// 64 = Cr stored onto the Cb plane (chroma store sectors halved).
+// 64 = Cr stored onto the Cb plane (chroma store sectors halved), 128 = chroma loaded in the pattern of a lane that
+// owns 4 columns of both planes.
 #ifndef H263_ABLATE
 #define H263_ABLATE 0
 #endif
@@ -143,7 +144,11 @@ __device__ __forceinline__ int round_q(float q, float m) { return __float2int_rz
 __device__ __forceinline__ void load_row3(const uint32_t* p, bool odd, bool third, bool row, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
 #if H263_LDG64
     const uint2* q = reinterpret_cast<const uint2*>(p - (odd ? 1 : 0));
-    const uint2 v0 = __ldg(q), v1 = __ldg(q + 1);
+    uint2 v0 = make_uint2(0u, 0u), v1 = make_uint2(0u, 0u);
+    if (row) {
+        v0 = __ldg(q);
+        if (third || odd) v1 = __ldg(q + 1);
+    }
     w0 = odd ? v0.y : v0.x, w1 = odd ? v1.x : v0.y, w2 = odd ? v1.y : v1.x;
 #else
     w0 = w1 = w2 = 0u;
@@ -652,6 +657,17 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 for (int r = 0; r < 3; r++) {
                     const uint32_t* p = src + (uint32_t)r * pitch_c4;
                     uint32_t w0, w1, w2;
+                    if (H263_ABLATE & 128) {
+                        // load pattern of a lane that owns 4 columns of BOTH planes (results wrong): 2 words per row and plane,
+                        // the two h lanes side by side in one sector
+                        const uint32_t* pb = reinterpret_cast<const uint32_t*>(pools.cb) + so + (uint32_t)(rg * 2 + r) * pitch_c4 + h;
+                        const uint32_t* pr = reinterpret_cast<const uint32_t*>(pools.cr) + so + (uint32_t)(rg * 2 + r) * pitch_c4 + h;
+                        w0 = w1 = w2 = 0u;
+                        if (r < 2 || wb != 0) {
+                            w0 = __ldg(pb), w2 = __ldg(pr);
+                            if ((fc & 7u) != 0) w1 = __ldg(pb + 1), w2 ^= __ldg(pr + 1);
+                        }
+                    } else
                     load_row3(p, odd, (fc & 7u) != 0, r < 2 || wb != 0, w0, w1, w2);
                     hs[r] = row_sum8(w0, w1, w2, sh, shb);
                 }
