@@ -65,7 +65,7 @@ assert C.sizeof(Pic) == 32 and C.sizeof(Mb) == 24
 # Every symbol include/h263cu.h declares; tests check that the library exports all of them.
 SYMBOLS = [
     "h263cu_is_eof_error", "h263cu_is_macroblock_error", "h263cu_is_gob_error", "h263cu_strerror",
-    "h263cu_version", "h263cu_parser_create", "h263cu_parser_destroy", "h263cu_parser_reset",
+    "h263cu_version", "h263cu_parser_create", "h263cu_parser_destroy", "h263cu_parser_options", "h263cu_parser_reset",
     "h263cu_peek_picture", "h263cu_parse_picture", "h263cu_parse_step", "h263cu_device_count",
     "h263cu_create", "h263cu_destroy", "h263cu_device_of", "h263cu_alloc_pinned", "h263cu_free_pinned",
     "h263cu_step_upload", "h263cu_step_free", "h263cu_step_run", "h263cu_submit_step",
@@ -96,6 +96,8 @@ def lib():
     L.h263cu_parser_create.restype = vp
     L.h263cu_parser_create.argtypes = [u32]
     L.h263cu_parser_destroy.argtypes = [vp]
+    L.h263cu_parser_options.restype = u32
+    L.h263cu_parser_options.argtypes = [vp]
     L.h263cu_parser_destroy.restype = None
     L.h263cu_parser_reset.argtypes = [vp]
     L.h263cu_parser_reset.restype = None

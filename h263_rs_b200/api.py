@@ -287,7 +287,8 @@ class BatchDecoder:
         bufs = [np.frombuffer(pk, np.uint8) if not isinstance(pk, np.ndarray) else pk for pk in packets]
         return {
             "n": n, "bufs": bufs, "ids": ids,
-            "parsers": (C.c_void_p * n)(*[self.parsers[int(s)].h for s in ids]),
+            # an id beyond the decoder's streams is passed on as it is: the library refuses the step
+            "parsers": (C.c_void_p * n)(*[self.parsers[min(int(s), self.n - 1)].h for s in ids]),
             "packets": (C.c_void_p * n)(*[b.ctypes.data for b in bufs]),
             "lens": (C.c_size_t * n)(*[b.size for b in bufs]),
             "errs": np.zeros(n, np.int32),

@@ -49,6 +49,7 @@ struct StreamState {
     uint8_t pic_type = 0, pquant = 0;
     uint16_t tr = 0;
     uint32_t stamp = 0;
+    uint32_t seen = 0;    // epoch of the last h263cu_decode_step that named this stream (duplicate check)
     bool padded = false;  // the last picture's planes carry the replicated border (tiled kernel)
 };
 
@@ -71,7 +72,7 @@ struct h263cu_ctx {
     size_t y_slot = 0, c_slot = 0, rgba_slot = 0;
     uint8_t *y_pool = nullptr, *cb_pool = nullptr, *cr_pool = nullptr, *rgba_pool = nullptr;
     std::vector<StreamState> streams;
-    uint32_t stamp = 0;
+    uint32_t stamp = 0, decode_epoch = 0;
     uint32_t rgba_parity = 0;
 
     cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -593,6 +594,20 @@ int h263cu_decode_step(h263cu_ctx* c, h263cu_parser* const* parsers, const uint8
     for (uint32_t i = 0; i < n; i++) bytes += lens[i];
     const size_t mb_need = (size_t)n * c->mbw * c->mbh, ev_need = bytes * 16 / 3 + 16 * (size_t)n;
     if (mb_need > 0xFFFFFFFFull || ev_need > 0xFFFFFFFFull) return H263CU_ERR_CAPACITY;
+    // Everything the device stage could refuse is checked before any parser advances, so that a failing call leaves
+    // every stream as it was (decode_next_picture is a transaction, state.rs:120-137): stream ids in range and named
+    // once, pictures no larger than the context.
+    c->decode_epoch++;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t sid = stream_ids ? stream_ids[i] : i;
+        if (sid >= c->max_streams) return H263CU_ERR_CAPACITY;
+        if (c->streams[sid].seen == c->decode_epoch) return H263CU_ERR_BAD_ARGUMENT;
+        c->streams[sid].seen = c->decode_epoch;
+        h263cu_pic hdr;
+        if (packets[i] && parsers[i] && h263cu_peek_picture(h263cu_parser_options(parsers[i]), packets[i], lens[i], &hdr) == 0 &&
+            (hdr.width > c->max_w || hdr.height > c->max_h))
+            return H263CU_ERR_CAPACITY;
+    }
     const int slot = c->ring_pos;  // the ring slot submit_common is about to use
     h263cu_ctx::Staging& st = c->staging[slot];
     // the copy engine has finished with this staging set (it was read two submits ago)

@@ -616,6 +616,7 @@ h263cu_parser* h263cu_parser_create(uint32_t decoder_options) {
     return p;
 }
 void h263cu_parser_destroy(h263cu_parser* p) { delete p; }
+uint32_t h263cu_parser_options(const h263cu_parser* p) { return p ? p->options : 0u; }
 void h263cu_parser_reset(h263cu_parser* p) {
     if (!p) return;
     p->has_last = p->has_reference = false;

@@ -138,6 +138,8 @@ typedef struct h263cu_parser h263cu_parser;
 /* H263State::new (state.rs:42-50): one parser per stream */
 h263cu_parser* h263cu_parser_create(uint32_t decoder_options);
 void h263cu_parser_destroy(h263cu_parser*);
+/* The DecoderOption bits the parser was created with */
+uint32_t h263cu_parser_options(const h263cu_parser*);
 /* Seek: discard all stream state; the next picture must be an I picture (state.rs:134-137) */
 void h263cu_parser_reset(h263cu_parser*);
 
@@ -213,7 +215,9 @@ int h263cu_submit_step_readback(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_
  * call returns as soon as the work is queued, so the parse of the next step overlaps this step's
  * kernels and copies.  Pictures that fail to parse are reported in per_pic_err[i] (may be NULL),
  * leave their stream untouched (the reference's transactional behaviour, state.rs:120-137) and are
- * left out of the step; *n_decoded (may be NULL) counts the rest.  When host_rgba is not NULL the
+ * left out of the step; *n_decoded (may be NULL) counts the rest.  What the device stage could refuse
+ * (stream id out of range or named twice, picture larger than the context) is checked before any parser
+ * advances: such a call fails as a whole and changes nothing.  When host_rgba is not NULL the
  * RGBA picture of input i is copied to host_rgba + i * rgba_stride (tight rows of 4 * width bytes)
  * on the read-back stream; call h263cu_sync before reading it. */
 int h263cu_decode_step(h263cu_ctx*, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,

@@ -292,6 +292,29 @@ def test_h263state_facade_surface():
         assert np.array_equal(st.get_reference_picture().as_chroma_r(), ref[i]["cr"])
 
 
+def test_decode_step_refuses_before_any_parser_advances():
+    """A step the device stage would refuse (picture larger than the context, a stream named twice, a stream id
+    out of range) fails as a whole and leaves parsers and streams untouched: the same packets decode afterwards."""
+    small = synth.make_stream(176, 144, 3, 31)
+    big = synth.make_stream(352, 288, 1, 32)
+    ref = oracle_decode_stream(small)
+    dec = api.BatchDecoder(2, 176, 144, threads=2)
+    with pytest.raises(_lib.H263Error) as e:
+        dec.decode_step([small[0], big[0]])
+    assert e.value.code == _lib.ERR_CAPACITY
+    with pytest.raises(_lib.H263Error) as e:
+        dec.decode_step([small[0], small[0]], stream_ids=[1, 1])
+    assert e.value.code == _lib.ERR_BAD_ARGUMENT
+    with pytest.raises(_lib.H263Error) as e:
+        dec.decode_step([small[0]], stream_ids=[7])
+    assert e.value.code == _lib.ERR_CAPACITY
+    for t in range(3):  # nothing advanced: stream 0 still starts at its I picture
+        assert not dec.decode_step([small[t]], stream_ids=[0]).any()
+        dec.ctx.sync()
+        y, cb, cr = dec.ctx.read_yuv(0)
+        assert np.array_equal(y, ref[t]["y"]) and np.array_equal(cb, ref[t]["cb"]) and np.array_equal(cr, ref[t]["cr"])
+
+
 def test_device_errors_are_loud():
     ctx = api.Context(0, 2, 176, 144)
     pk = synth.make_stream(352, 288, 1, 1)
