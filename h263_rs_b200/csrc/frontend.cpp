@@ -9,7 +9,11 @@
 // transactional "nothing changes on failure" contract follow the reference.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
+#include <pthread.h>
 #include <thread>
 #include <vector>
 
@@ -607,6 +611,74 @@ static inline void commit(h263cu_parser* p, const PendingState& s) {
 
 }  // namespace
 
+namespace {
+// Persistent worker threads for h263cu_parse_step: a step is parsed every few milliseconds, and creating and joining
+// 2 x (threads - 1) std::threads per step cost a sixth of the parse itself.  One job at a time (callers serialise on
+// the job mutex); the workers are detached and live until the process ends.
+class WorkerPool {
+  public:
+    // runs fn on `threads` threads (the caller is one of them) and returns when all have finished
+    void run(int threads, const std::function<void()>& fn) {
+        if (threads <= 1) {
+            fn();
+            return;
+        }
+        std::lock_guard<std::mutex> job(job_mutex_);
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            while ((int)n_workers_ < threads - 1) {
+                std::thread(&WorkerPool::worker, this, n_workers_).detach();
+                n_workers_++;
+            }
+            fn_ = &fn;
+            wanted_ = threads - 1;
+            running_ = threads - 1;
+            generation_++;
+        }
+        cv_.notify_all();
+        fn();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return running_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void worker(size_t index) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void()>* fn;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if ((int)index >= wanted_) continue;  // this job uses fewer workers
+                fn = fn_;
+            }
+            (*fn)();
+            std::lock_guard<std::mutex> lk(m_);
+            if (--running_ == 0) done_.notify_all();
+        }
+    }
+    std::mutex job_mutex_, m_;
+    std::condition_variable cv_, done_;
+    const std::function<void()>* fn_ = nullptr;
+    size_t n_workers_ = 0;
+    int wanted_ = 0, running_ = 0;
+    uint64_t generation_ = 0;
+};
+// never destroyed: the detached workers may outlive static destructors.  Threads do not survive fork(): the child
+// starts with a fresh pool (the old object, with its possibly locked mutexes, is abandoned).
+WorkerPool* g_pool = nullptr;
+std::once_flag g_pool_once;
+WorkerPool& worker_pool() {
+    std::call_once(g_pool_once, [] {
+        g_pool = new WorkerPool();
+        pthread_atfork(nullptr, nullptr, [] { g_pool = new WorkerPool(); });
+    });
+    return *g_pool;
+}
+}  // namespace
+
 extern "C" {
 
 h263cu_parser* h263cu_parser_create(uint32_t decoder_options) {
@@ -688,12 +760,7 @@ int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packe
             p->st_err = e;
         }
     };
-    {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < threads; t++) pool.emplace_back(work1);
-        work1();
-        for (auto& th : pool) th.join();
-    }
+    worker_pool().run(threads, work1);
 
     // phase 2: pack the successful pictures densely
     uint32_t np = 0, nm = 0, nu = 0;
@@ -730,12 +797,7 @@ int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packe
             commit(p, pend[i]);
         }
     };
-    {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < threads; t++) pool.emplace_back(work2);
-        work2();
-        for (auto& th : pool) th.join();
-    }
+    worker_pool().run(threads, work2);
     if (pic_of_input) std::memcpy(pic_of_input, packed.data(), n * sizeof(int32_t));
     *n_pics_out = np;
     *n_mbs_out = nm;

@@ -70,7 +70,7 @@ def test_two_gloo_ranks_reproduce_the_unsharded_parse():
     import torch.multiprocessing as mp
 
     world, port = 2, 29533 + os.getpid() % 200
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # no fork: the parser library keeps worker threads
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     expect = stream_checksums(np.arange(N_STREAMS))
