@@ -251,7 +251,7 @@ def run_reference(args, rank):
         "gpu_launches": 0,
         "setup_s": {"generate": round(gen_s, 2)},
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---------------------------------------------------------------------------- GPU arm
@@ -494,7 +494,7 @@ def run_ours(args, rank, world, local_rank, dist):
         "setup_s": setup,
     }
     out.update(extras)
-    print(json.dumps(out))
+    emit(out)
 
 
 def parity_check(ctx, blobs, total, n_check):
@@ -613,8 +613,30 @@ def ncu_traffic():
     return None
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath (NCCL's version banner, CUDA warnings) write to
+    file descriptor 1 as well: keep the real stdout aside and point fd 1 at stderr for the rest of the run."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if _REAL_STDOUT is not None:
+        _REAL_STDOUT.write(line + "\n")
+        _REAL_STDOUT.flush()
+    else:
+        print(line)
+
+
 def main():
     args = parse_args()
+    guard_stdout()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
