@@ -190,7 +190,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     const bool want_deblock = want_rgba && (out_flags & H263CU_OUT_DEBLOCK) != 0;
     c->stamp++;
     uint32_t max_w = 0, max_h = 0;
-    bool tiled = true, aligned16 = true;
+    bool tiled = true, aligned16 = true, wide_mv = false;
     for (uint32_t i = 0; i < n; i++) {
         const h263cu_pic& p = s->pics[i];
         if (p.stream >= c->max_streams) return H263CU_ERR_CAPACITY;
@@ -213,6 +213,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         // the tiled kernel needs references with a replicated border; sizes that are not multiples of 16 take its
         // edge fix-up instantiation, and the register-resident deblock kernel needs aligned pictures
         if ((p.width | p.height) & 15) aligned16 = false;
+        if ((p.flags & H263CU_PICFLAG_HAS_INTER) && !(p.flags & H263CU_PICFLAG_MV_IN_RANGE)) wide_mv = true;
         if ((p.flags & H263CU_PICFLAG_HAS_INTER) && !st.padded) tiled = false;
     }
     if (c->force_kernel == 1) tiled = false;
@@ -267,7 +268,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     cudaEvent_t pa = nullptr, pb = nullptr;
     if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
     const Pools pools{c->y_pool, c->cb_pool, c->cr_pool, c->rgba_pool, c->d_work_counter, c->pitch_y, c->pitch_c, c->rgba_pitch};
-    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? (aligned16 ? 1 : 2) : 0, pools,
+    launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? (aligned16 ? 1 : 2) : 0, wide_mv, pools,
                  c->s_main);
     c->launches++;
     if (tiled) c->tiled_launches++;

@@ -352,6 +352,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
     uint32_t n = 0;        // macroblocks decoded so far (may exceed capacity with trailing COD=1 bits)
     uint32_t ev_used = 0;  // event units written
     bool any_inter = false;
+    bool mv_in_range = true;  // halfpel_decode wraps every component into [-32, 31] (mvd_pred.rs:70-117); checked anyway
     uint8_t ev_run[6][64];
     int16_t ev_level[6][64];
 
@@ -513,6 +514,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                 int px = median3(c1.x, c2.x, c3.x), py = median3(c1.y, c2.y, c3.y);
                 cur[k].x = (int8_t)wrap_mv(px, mvd[k].x);
                 cur[k].y = (int8_t)wrap_mv(py, mvd[k].y);
+                mv_in_range &= cur[k].x >= -32 && cur[k].x <= 31 && cur[k].y >= -32 && cur[k].y <= 31;
             }
             if (!four) cur[1] = cur[2] = cur[3] = cur[0];
             any_inter = true;
@@ -584,7 +586,8 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
     pic->mb_w = (uint8_t)mb_w, pic->mb_h = (uint8_t)mb_h;
     pic->pic_type = hd.pic_type;
     pic->pquant = hd.quant;
-    pic->flags = (uint8_t)((hd.deblock ? H263CU_PICFLAG_DEBLOCK : 0) | (any_inter ? H263CU_PICFLAG_HAS_INTER : 0));
+    pic->flags = (uint8_t)((hd.deblock ? H263CU_PICFLAG_DEBLOCK : 0) | (any_inter ? H263CU_PICFLAG_HAS_INTER : 0) |
+                           (mv_in_range ? H263CU_PICFLAG_MV_IN_RANGE : 0));
     pic->version = hd.version < 0 ? 0xFF : (uint8_t)hd.version;
     pic->first_mb = mb_base;
     pic->n_mbs = capacity;

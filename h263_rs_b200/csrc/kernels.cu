@@ -288,10 +288,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 }
 
 void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs, int emit_rgba,
-                  int tiled, const Pools& pools, cudaStream_t stream) {
+                  int tiled, int wide_mv, const Pools& pools, cudaStream_t stream) {
     if (n_mbs == 0) return;
     if (tiled) {
-        launch_recon_tile(pics, mbs, events, n_mbs, emit_rgba, tiled == 2, pools, stream);
+        launch_recon_tile(pics, mbs, events, n_mbs, emit_rgba, tiled == 2, wide_mv, pools, stream);
     } else {
         const uint32_t grid = (n_mbs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         recon_mb_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba);

@@ -45,11 +45,12 @@ struct Pools {
 // tiled != 0 selects recon_tile_kernel (padded reference planes), else the generic warp-per-macroblock
 // recon_mb_kernel.
 // tiled: 1 = every picture is a multiple of 16 in size, 2 = some are not (edge fix-up instantiation).
+// wide_mv: some picture of the step may hold vectors beyond [-32, 31] half-pel units (no H263CU_PICFLAG_MV_IN_RANGE).
 void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
-                  int emit_rgba, int tiled, const Pools& pools, cudaStream_t stream);
+                  int emit_rgba, int tiled, int wide_mv, const Pools& pools, cudaStream_t stream);
 // recon_tile.cu
 void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
-                       int emit_rgba, int unaligned, const Pools& pools, cudaStream_t stream);
+                       int emit_rgba, int unaligned, int wide_mv, const Pools& pools, cudaStream_t stream);
 
 // Plane padding (bytes / rows) reserved around every reconstruction plane: the tiled kernel
 // replicates 16 luma / 8 chroma border pixels into it; the extra columns keep the interior

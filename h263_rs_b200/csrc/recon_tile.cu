@@ -237,7 +237,10 @@ __device__ __forceinline__ uint32_t splat_hi(uint32_t w) { return __byte_perm(w,
 // macroblock column / row that lies outside the picture is overwritten with the picture's edge pixels before the
 // stores (and the border replication continues from there), so that prediction reads beyond the true edge see
 // read_sample's clamp (gather.rs:16-31).  Compiled out of the instantiations for aligned pictures.
-template <int PY, int PC, int PR, bool EDGE>
+// WIDE_MV: some vector of the step may leave the replicated border (no H263CU_PICFLAG_MV_IN_RANGE; unreachable from a
+// parsed stream, mvd_pred.rs:70-117): the instantiation with the clamped per-sample path.  Without it vectors are
+// clamped to the range in phase 0, and the 900 instructions of that path do not weigh on the register allocation.
+template <int PY, int PC, int PR, bool EDGE, bool WIDE_MV>
 __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
     recon_tile_kernel(const PicDev* __restrict__ pics, const h263cu_mb* __restrict__ mbs,
                       const h263cu_event* __restrict__ events, uint32_t n_mbs, int emit_rgba, const Pools pools) {
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             if (bb < 4) {
                 // mv[bb] = bytes 2bb, 2bb+1 of (w4, w5), sign-extended
                 mvx = (int)(int8_t)__byte_perm(w4, w5, 0x4440u + 2u * (uint32_t)bb), mvy = (int)(int8_t)__byte_perm(w4, w5, 0x4441u + 2u * (uint32_t)bb);
+                if (!WIDE_MV) mvx = max(min(mvx, 31), -32), mvy = max(min(mvy, 31), -32);
                 in_range = mvx >= -32 && mvx <= 31 && mvy >= -32 && mvy <= 31;
                 sx = mbx * 16 + (bb & 1) * 8 + (mvx >> 1), sy = mby * 16 + (bb >> 1) * 8 + (mvy >> 1);
                 pitch = PY ? PY : P.pitch_y, base = P.ref_y4;
@@ -306,13 +310,14 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 const int sumx = (int8_t)byte_of(w4, 0) + (int8_t)byte_of(w4, 2) + (int8_t)byte_of(w5, 0) + (int8_t)byte_of(w5, 2);
                 const int sumy = (int8_t)byte_of(w4, 1) + (int8_t)byte_of(w4, 3) + (int8_t)byte_of(w5, 1) + (int8_t)byte_of(w5, 3);
                 mvx = average_sum_of_mvs(sumx), mvy = average_sum_of_mvs(sumy);
+                if (!WIDE_MV) mvx = max(min(mvx, 15), -16), mvy = max(min(mvy, 15), -16);
                 in_range = mvx >= -16 && mvx <= 15 && mvy >= -16 && mvy <= 15;
                 sx = mbx * 8 + (mvx >> 1), sy = mby * 8 + (mvy >> 1);
                 pitch = PC ? PC : P.pitch_c, base = P.ref_c4;
             }
             const int a = sx & 3;
             boff = base + (uint32_t)((sy * pitch + (sx - a)) >> 2);
-            bflags = (uint32_t)(a | ((mvx & 1) << 2) | ((mvy & 1) << 3)) | (in_range ? 0u : BF_SLOW);
+            bflags = (uint32_t)(a | ((mvx & 1) << 2) | ((mvy & 1) << 3)) | (!WIDE_MV || in_range ? 0u : BF_SLOW);
 #if H263_PREFETCH_L2
             // the 9 source rows of this block (reference planes are DRAM-resident: written a step ago):
             // start the DRAM -> L2 transfer now, the epilogue loads them ~1000 instructions later
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         RowSum cy[2];  // chroma (own plane): 2 rows x 8 pixels
         if (flags & MBF_INTER) {
             const uint32_t fl = W.bf[bl], fc = W.bf[bc];
-            if (!(fl & BF_SLOW)) {
+            if (!WIDE_MV || !(fl & BF_SLOW)) {
                 const int sh = (fl & 3u) * 8, shb = sh + ((fl & 4u) << 1);
                 const uint32_t wb = (fl >> 3) & 1u, wt = 2u - wb;
                 const uint32_t so = W.bd[bl];
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     ly[rr].e1 = __byte_perm(o1, 0, 0x4240), ly[rr].o1 = __byte_perm(o1, 0, 0x4341);
                 }
             }
-            if (!(fc & BF_SLOW)) {
+            if (!WIDE_MV || !(fc & BF_SLOW)) {
                 const int sh = (fc & 3u) * 8, shb = sh + ((fc & 4u) << 1);
                 const uint32_t wb = (fc >> 3) & 1u, wt = 2u - wb;
                 // chroma rows 2*rg, 2*rg+1 of the macroblock, all 8 columns, plane h
@@ -933,7 +938,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
 }
 
 void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs, int emit_rgba,
-                       int unaligned, const Pools& pools, cudaStream_t stream) {
+                       int unaligned, int wide_mv, const Pools& pools, cudaStream_t stream) {
     if (n_mbs == 0) return;
     const uint32_t per_cta = CTA_WARPS * WARP_MBS;
     uint32_t grid = (n_mbs + per_cta * kTilesPerWarp - 1) / (per_cta * kTilesPerWarp);
@@ -948,16 +953,21 @@ void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_ev
     }
     // pitches of the standard formats (context.cu: pitch_y = 16*mbw + 64, pitch_c = round_up(8*mbw + 32, 16))
     const uint32_t py = pools.pitch_y, pc = pools.pitch_c, pr = pools.rgba_pitch;
-    if (unaligned)  // some picture of the step is not a multiple of 16 in size: edge fix-up, run-time pitches
-        recon_tile_kernel<0, 0, 0, true><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+    if (wide_mv) {  // hand-built side info with vectors beyond the range: clamped per-sample path, run-time pitches
+        if (unaligned)
+            recon_tile_kernel<0, 0, 0, true, true><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+        else
+            recon_tile_kernel<0, 0, 0, false, true><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+    } else if (unaligned)  // some picture of the step is not a multiple of 16 in size: edge fix-up, run-time pitches
+        recon_tile_kernel<0, 0, 0, true, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
     else if (py == 416 && pc == 208 && pr == 1408)  // CIF 352x288
-        recon_tile_kernel<416, 208, 1408, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+        recon_tile_kernel<416, 208, 1408, false, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
     else if (py == 240 && pc == 128 && pr == 704)  // QCIF 176x144
-        recon_tile_kernel<240, 128, 704, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+        recon_tile_kernel<240, 128, 704, false, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
     else if (py == 768 && pc == 384 && pr == 2816)  // 4CIF 704x576
-        recon_tile_kernel<768, 384, 2816, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+        recon_tile_kernel<768, 384, 2816, false, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
     else
-        recon_tile_kernel<0, 0, 0, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
+        recon_tile_kernel<0, 0, 0, false, false><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools);
 }
 
 }  // namespace h263dev

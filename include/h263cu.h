@@ -87,6 +87,12 @@ int h263cu_version(void);
 
 #define H263CU_PICFLAG_DEBLOCK 1u   /* Sorenson DeblockingFlag (advisory, picture.rs:319-325) */
 #define H263CU_PICFLAG_HAS_INTER 2u /* at least one MB needs the reference picture */
+/* Every motion vector component of the picture lies in [-32, 31] half-pel units.  Always true for a stream decoded by
+ * the front end: halfpel_decode (mvd_pred.rs:70-117) wraps into that range, and the extended range is unreachable
+ * because the running options stay empty (state.rs:152-155).  When every picture of a step carries the flag the
+ * device runs the reconstruction kernel without the clamped per-sample prediction path.  A producer that sets the
+ * flag on a picture with longer vectors gets them clamped to the range. */
+#define H263CU_PICFLAG_MV_IN_RANGE 4u
 
 typedef struct h263cu_pic { /* 32 bytes */
     uint32_t stream;        /* stream slot inside the context, < max_streams */

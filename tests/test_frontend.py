@@ -114,6 +114,7 @@ def test_parse_step_threaded_matches_serial():
             assert errs[s] == 0 and pic_of[s] == k
             p = pics[k]
             assert p["stream"] == s and p["n_mbs"] == len(m) and p["n_event_units"] == len(ev)
+            assert p["flags"] & 4  # H263CU_PICFLAG_MV_IN_RANGE: parsed vectors never leave [-32, 31]
             got_m = mbs[p["first_mb"] : p["first_mb"] + p["n_mbs"]].copy()
             assert (got_m["pic"] == k).all()
             got_m["pic"] = 0

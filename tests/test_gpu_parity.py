@@ -360,3 +360,78 @@ def test_tiled_and_generic_kernels_agree_and_interleave(monkeypatch):
                 assert np.array_equal(ctx.read_rgba(1), rb[tb]["rgba"])
                 tb += 1
         ctx.close()
+
+
+def _decode_with_records(monkeypatch, force, packets_by_stream, dims, edit):
+    """Decodes the streams in lock step through submit_step; `edit(t, pics, mbs)` may rewrite the side info of a step."""
+    if force:
+        monkeypatch.setenv("H263CU_KERNEL", force)
+    else:
+        monkeypatch.delenv("H263CU_KERNEL", raising=False)
+    n = len(packets_by_stream)
+    ctx = api.Context(0, n, max(d[0] for d in dims), max(d[1] for d in dims))
+    parsers = [frontend.Parser(1) for _ in range(n)]
+    out = []
+    for t in range(len(packets_by_stream[0])):
+        pics, mbs, events, errs, _ = frontend.parse_step(parsers, [p[t] for p in packets_by_stream], list(range(n)), 2)
+        assert not errs.any()
+        edit(t, pics, mbs)
+        ctx.submit_step(pics, mbs, events, _lib.OUT_RGBA)
+        ctx.sync()
+        out.append([(ctx.read_yuv(s), ctx.read_rgba(s)) for s in range(n)])
+    launches = (ctx.launch_count(), ctx.tiled_launch_count())
+    ctx.close()
+    return out, launches
+
+
+PICFLAG_MV_IN_RANGE = 4
+
+
+def test_vectors_beyond_the_range_take_the_clamped_path(monkeypatch):
+    """Hand-built side info may hold vectors the front end never emits (beyond [-32, 31] half-pel units; the
+    parser's own are always inside, mvd_pred.rs:70-117, and it says so with H263CU_PICFLAG_MV_IN_RANGE).  Without the
+    flag the tiled kernel runs its instantiation with the clamped per-sample prediction (read_sample,
+    gather.rs:16-31) and must agree bit for bit with the generic warp-per-macroblock kernel; aligned and unaligned
+    picture sizes.  With the flag set falsely the step still runs and every untouched macroblock is unchanged."""
+    dims = [(352, 288), (200, 100)]
+    streams = [synth.make_stream(w, h, 4, 900 + i, mv_mode=2, pct_fourmv=20) for i, (w, h) in enumerate(dims)]
+    rng = np.random.default_rng(5)
+    picks = {}
+
+    def edit(keep_flag):
+        def f(t, pics, mbs):
+            assert (pics["flags"] & PICFLAG_MV_IN_RANGE).all()  # the parser vouches for its vectors
+            if t == 0:
+                return
+            inter = np.flatnonzero((mbs["flags"] & _lib.MB_INTER) != 0)
+            if t not in picks:
+                idx = rng.choice(inter, size=min(60, len(inter)), replace=False)
+                picks[t] = (idx, rng.integers(-120, 121, size=(len(idx), 8)).astype(np.int8))
+            idx, mv = picks[t]
+            mbs["u"][idx] = mv.view(np.uint8)
+            if not keep_flag:
+                pics["flags"] &= np.uint8(~PICFLAG_MV_IN_RANGE & 0xFF)
+        return f
+
+    tiled, (n_launch, n_tiled) = _decode_with_records(monkeypatch, None, streams, dims, edit(False))
+    assert n_tiled == n_launch  # the tiled kernel ran, in its WIDE_MV instantiation
+    generic, _ = _decode_with_records(monkeypatch, "mb", streams, dims, edit(False))
+    for t in range(len(tiled)):
+        for s in range(len(dims)):
+            (ya, ca, ra), rgba_a = tiled[t][s]
+            (yb, cb_, rb), rgba_b = generic[t][s]
+            assert np.array_equal(ya, yb) and np.array_equal(ca, cb_) and np.array_equal(ra, rb), (t, s)
+            assert np.array_equal(rgba_a, rgba_b), (t, s)
+    # flag set falsely: defined behaviour is "runs, reads stay inside the planes"; picture 1 differs from the exact
+    # result only inside the macroblocks whose vectors were rewritten
+    lied, _ = _decode_with_records(monkeypatch, None, streams, dims, edit(True))
+    (y1, _, _), _ = lied[1][0]
+    (y2, _, _), _ = tiled[1][0]
+    diff = np.argwhere(np.asarray(y1).reshape(288, 352) != np.asarray(y2).reshape(288, 352))
+    assert len(diff) > 0  # the clamped vectors do change those macroblocks
+    idx, _ = picks[1]
+    touched = set()
+    for k in idx:
+        if k < 396:  # records of stream 0 (CIF, 22 x 18 macroblocks) come first in the step
+            touched.add((int(k) // 22, int(k) % 22))
+    assert all((int(r) // 16, int(c) // 16) in touched for r, c in diff)
