@@ -83,6 +83,51 @@ __global__ void __launch_bounds__(CTA_WARPS * 32) fetch_ldg(const Rec* __restric
     out[(size_t)tile * 32 + lane] = acc;
 }
 
+// ---- C: direct loads with another division of the macroblock: a lane owns 4 luma columns x 8 rows and the 2 x 4
+// chroma samples of BOTH planes under them (4 lanes side by side in a row): fewer distinct sectors per load pass
+// (8 rows per pass instead of 16 for luma, 8 instead of 32 for chroma), more passes.  Throughput probe only (its
+// reduction is over a different partition of the same bytes, so its words are not comparable with A's).
+__global__ void __launch_bounds__(CTA_WARPS * 32) fetch_ldg_4x8(const Rec* __restrict__ recs, const uint8_t* __restrict__ y,
+                                                               const uint8_t* __restrict__ cb, const uint8_t* __restrict__ cr,
+                                                               uint32_t n_mbs, uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * CTA_WARPS + warp;
+    const int mbq = lane >> 3, half = (lane >> 2) & 1, q = lane & 3;
+    const uint32_t mb = tile * WARP_MBS + mbq;
+    if (mb >= n_mbs) return;
+    const Rec r = recs[mb];
+    uint32_t acc = 0;
+    {
+        const uint32_t col = r.ycol + 4 * q, a = col & 3;
+        const bool second = a != 0 || (r.hp & 1u), extra = (r.hp & 2u) != 0;
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(y + (size_t)(r.yrow + half * 8) * PITCH_Y + (col - a));
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const uint32_t* q0 = p + k * (PITCH_Y / 4);
+            if (k < 8 || extra) {
+                const uint32_t w0 = __ldg(q0), w1 = second ? __ldg(q0 + 1) : 0u;
+                acc ^= __funnelshift_r(w0, w1, a * 8) ^ ((w1 >> (a * 8)) & 0xFFu);
+            }
+        }
+    }
+    {
+        const uint32_t col = r.ccol + 2 * q, a = col & 3;
+        const bool second = a + 2 + ((r.hp >> 2) & 1u) > 4, extra = (r.hp & 8u) != 0;
+        const size_t off = (size_t)(r.crow + half * 4) * PITCH_C + (col - a);
+        const uint32_t* pb = reinterpret_cast<const uint32_t*>(cb + off);
+        const uint32_t* pr = reinterpret_cast<const uint32_t*>(cr + off);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            if (k < 4 || extra) {
+                const uint32_t b0 = __ldg(pb + k * (PITCH_C / 4)), r0 = __ldg(pr + k * (PITCH_C / 4));
+                const uint32_t b1 = second ? __ldg(pb + k * (PITCH_C / 4) + 1) : 0u, r1 = second ? __ldg(pr + k * (PITCH_C / 4) + 1) : 0u;
+                acc ^= (__funnelshift_r(b0, b1, a * 8) & 0xFFFFFFu) ^ (__funnelshift_r(r0, r1, a * 8) & 0xFFFFFFu);
+            }
+        }
+    }
+    out[(size_t)tile * 32 + lane] = acc;
+}
+
 // ---- B: TMA boxes into shared memory ----------------------------------------------------------------------------
 constexpr int LUMA_BOX_W = 48, LUMA_BOX_H = 17, CHROMA_BOX_W = 32, CHROMA_BOX_H = 9;
 constexpr int LUMA_BYTES = LUMA_BOX_W * LUMA_BOX_H;        // 816
@@ -223,7 +268,8 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_recs, recs.size() * sizeof(Rec)));
     CK(cudaMemcpy(d_recs, recs.data(), recs.size() * sizeof(Rec), cudaMemcpyHostToDevice));
     const uint32_t n_tiles = (n_mbs + WARP_MBS - 1) / WARP_MBS, grid = (n_tiles + CTA_WARPS - 1) / CTA_WARPS;
-    uint32_t *out_a, *out_b;
+    uint32_t *out_a, *out_b, *out_c;
+    CK(cudaMalloc(&out_c, (size_t)n_tiles * 32 * 4));
     CK(cudaMalloc(&out_a, (size_t)n_tiles * 32 * 4));
     CK(cudaMalloc(&out_b, (size_t)n_tiles * 32 * 4));
     CK(cudaMemset(out_a, 0, (size_t)n_tiles * 32 * 4));
@@ -254,19 +300,22 @@ int main(int argc, char** argv) {
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     const int warm = 3, reps = 20;
-    float ms_a = 0, ms_b = 0;
-    for (int v = 0; v < 2; v++) {
+    float ms_a = 0, ms_b = 0, ms_c = 0;
+    CK(cudaFuncSetAttribute(fetch_ldg_4x8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    for (int v = 0; v < 3; v++) {
         for (int i = 0; i < warm + reps; i++) {
             if (i == warm) CK(cudaEventRecord(e0));
             if (v == 0)
                 fetch_ldg<<<grid, CTA_WARPS * 32, smem_a>>>(d_recs, y, cb, cr, n_mbs, out_a);
+            else if (v == 2)
+                fetch_ldg_4x8<<<grid, CTA_WARPS * 32, smem_a>>>(d_recs, y, cb, cr, n_mbs, out_c);
             else
                 fetch_tma<<<grid, CTA_WARPS * 32, smem_b>>>(d_recs, tm_y, tm_cb, tm_cr, n_mbs, out_b);
         }
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         CK(cudaGetLastError());
-        CK(cudaEventElapsedTime(v == 0 ? &ms_a : &ms_b, e0, e1));
+        CK(cudaEventElapsedTime(v == 0 ? &ms_a : (v == 1 ? &ms_b : &ms_c), e0, e1));
     }
     std::vector<uint32_t> ha((size_t)n_tiles * 32), hb((size_t)n_tiles * 32);
     CK(cudaMemcpy(ha.data(), out_a, ha.size() * 4, cudaMemcpyDeviceToHost));
@@ -279,6 +328,8 @@ int main(int argc, char** argv) {
            ms_a / reps * 1e3, window_bytes / (ms_a / reps * 1e-3) / 1e9);
     printf("B  TMA boxes (48x17 + 2 x 32x9 per macroblock, 16-byte aligned starts) + LDS, %d CTAs/SM : %.1f us per launch  (%.0f GB/s of window bytes)\n", ctas_b,
            ms_b / reps * 1e3, window_bytes / (ms_b / reps * 1e-3) / 1e9);
+    printf("C  per-lane aligned LDG, lane = 4 columns x 8 rows + both chroma planes, %d CTAs/SM : %.1f us per launch  (%.0f GB/s of window bytes)\n",
+           ctas_a, ms_c / reps * 1e3, window_bytes / (ms_c / reps * 1e-3) / 1e9);
     printf("results %s (%zu of %zu words differ)\n", bad ? "DIFFER" : "identical", bad, ha.size());
     return bad ? 2 : 0;
 }
