@@ -260,7 +260,9 @@ def run_ours(args, rank, world, local_rank, dist):
 
     from h263_rs_b200 import _lib, api, frontend, shard
 
-    threads = max(1, host_threads() // max(world, 1))
+    # each rank keeps its parser threads and its pinned staging on the socket its GPU hangs off
+    placement = shard.bind_rank_to_gpu_node(local_rank, world) if world > 1 else {"numa_node": None, "cpus": None}
+    threads = placement["cpus"] or max(1, host_threads() // max(world, 1))
     S = args.streams
     U = args.unique if args.unique and args.unique < S else S
     total = args.warmup + args.steps + 1  # step 0 = I pictures
@@ -473,7 +475,7 @@ def run_ours(args, rank, world, local_rank, dist):
         "frames_per_s": value * 1e6 / (W * H),
         "e2e": {"value": bit_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rgba_bytes,
                 "ms_per_step": 1e3 * bit_max / max(args.steps, 1), "readback_matches_device": bit_ok,
-                "bitstream_bytes_per_step": int(bitstream_bytes / max(args.steps, 1)), "parse_threads": threads,
+                "bitstream_bytes_per_step": int(bitstream_bytes / max(args.steps, 1)), "parse_threads": threads, "host_placement": placement,
                 "path": "h263cu_decode_step: bitstream packets in host memory -> threaded VLC parse into pinned staging -> "
                         "H2D side info -> recon kernel -> D2H RGBA into pinned host memory, steps pipelined"},
         "e2e_from_side_info": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rgba_bytes,

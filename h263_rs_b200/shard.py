@@ -73,3 +73,84 @@ def interleave_shards(parts, n_streams):
         ids = shard_streams(n_streams, world, r)
         out[ids] = p[: len(ids)]
     return out
+
+
+# ---- host placement ---------------------------------------------------------------------------
+# The path never exchanges data between GPUs, but every rank moves ~420 MB of RGBA per step into
+# pinned host memory and runs its own parser threads.  On a two-socket box that traffic should stay
+# on the socket the GPU hangs off: a rank whose threads and pinned buffers sit on the other socket
+# pays the inter-socket link on every byte.
+
+def _parse_cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index):
+    """NUMA node of a CUDA device from sysfs, or None when the platform does not tell."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def node_cpus(node):
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            return _parse_cpulist(f.read())
+    except Exception:
+        return []
+
+
+def plan_cpu_slices(nodes, allowed, cpus_of_node):
+    """CPU set per local rank.  `nodes[r]` = NUMA node of rank r's GPU (None = unknown), `allowed`
+    = CPUs this job may use, `cpus_of_node(n)` = CPUs of node n.  Ranks on the same node split its
+    allowed CPUs evenly; ranks without a node (or whose node has no allowed CPU) split what is left
+    of an even share of everything.  Pure function: tested on CPU."""
+    world = len(nodes)
+    allowed = sorted(allowed)
+    out = [None] * world
+    by_node = {}
+    for r, n in enumerate(nodes):
+        cpus = [c for c in cpus_of_node(n) if c in set(allowed)] if n is not None else []
+        if cpus:
+            by_node.setdefault(n, (cpus, []))[1].append(r)
+    for n, (cpus, ranks) in by_node.items():
+        k = len(ranks)
+        for i, r in enumerate(ranks):
+            share = cpus[i * len(cpus) // k:(i + 1) * len(cpus) // k]
+            out[r] = share or cpus
+    for r in range(world):
+        if out[r] is None:
+            share = allowed[r * len(allowed) // world:(r + 1) * len(allowed) // world]
+            out[r] = share or allowed
+    return out
+
+
+def bind_rank_to_gpu_node(local_rank, local_world):
+    """Pins the calling thread (and the threads and pinned allocations it makes afterwards) to this
+    rank's share of the CPUs of its GPU's NUMA node.  Returns a dict describing what was done."""
+    import os
+
+    if not hasattr(os, "sched_setaffinity"):
+        return {"numa_node": None, "cpus": None}
+    allowed = sorted(os.sched_getaffinity(0))
+    nodes = [gpu_numa_node(r) for r in range(local_world)]
+    slices = plan_cpu_slices(nodes, allowed, node_cpus)
+    mine = slices[local_rank]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return {"numa_node": nodes[local_rank], "cpus": None}
+    return {"numa_node": nodes[local_rank], "cpus": len(mine)}

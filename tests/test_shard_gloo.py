@@ -76,3 +76,24 @@ def test_two_gloo_ranks_reproduce_the_unsharded_parse():
     expect = stream_checksums(np.arange(N_STREAMS))
     assert np.array_equal(np.asarray(ret["sums"]), expect)
     assert ret["t_max"] == 11.0 and ret["units"] == float(N_STREAMS)
+
+
+def test_plan_cpu_slices():
+    """Ranks split the CPUs of their GPU's NUMA node; ranks without node information share evenly."""
+    from h263_rs_b200 import shard
+
+    cpus = {0: list(range(0, 16)), 1: list(range(16, 32))}
+    plan = shard.plan_cpu_slices([0, 0, 1, 1], range(32), lambda n: cpus[n])
+    assert plan == [list(range(0, 8)), list(range(8, 16)), list(range(16, 24)), list(range(24, 32))]
+    # all GPUs on node 1, job restricted to a subset of the CPUs
+    plan = shard.plan_cpu_slices([1, 1], [4, 5, 20, 21, 22, 23], lambda n: cpus[n])
+    assert plan == [[20, 21], [22, 23]]
+    # unknown placement: an even share of everything, never empty
+    plan = shard.plan_cpu_slices([None, None, None], range(4), lambda n: [])
+    assert all(plan) and sorted(sum(plan, [])) == [0, 1, 2, 3]
+    plan = shard.plan_cpu_slices([None] * 8, range(2), lambda n: [])
+    assert all(plan)
+    # a node none of whose CPUs is allowed falls back to the even share
+    plan = shard.plan_cpu_slices([0, 1], range(16, 32), lambda n: cpus[n])
+    assert plan[1] == list(range(16, 32)) and plan[0] == list(range(16, 24))
+    assert shard._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
