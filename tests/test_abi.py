@@ -60,3 +60,22 @@ def test_no_cpu_fallback_without_a_device():
     out = np.zeros(64, np.uint8)
     assert L.h263cu_yuv420_to_rgba(y.ctypes.data, y.ctypes.data, y.ctypes.data, 16, 4, out.ctypes.data) == _lib.ERR_NO_DEVICE
     assert L.h263cu_deblock(y.ctypes.data, 16, 4, 3, out.ctypes.data) == _lib.ERR_NO_DEVICE
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (Python, C++, CUDA) names it, and the shipped
+    library neither links nor embeds it."""
+    import os
+    import subprocess
+
+    pkg = os.path.dirname(_lib.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".inc", ".h")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                for needle in ("oracle/", "oracle_lib", "liboracle", "import oracle", "h263_oracle", "orc_"):
+                    assert needle not in text, (os.path.join(root, f), needle)
+    needed = subprocess.run(["readelf", "-d", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in needed.lower()
+    syms = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert " orc_" not in syms
