@@ -543,8 +543,41 @@ def single_stream(api, frontend, device):
     for st in steps:
         ctx.step_free(st)
     fps = (n - 20) / (ms * 1e-3)
+    ctx.close()
+    # the same stream the way a player drives the reference: H263State::decode_next_picture per packet, then the RGBA
+    # of that picture in host memory before the next packet is touched (parse + upload + kernel + read-back, serial)
+    state = api.H263State(device=device)
+    for pk in packets[:20]:
+        state.decode_next_picture(pk)
+        state.get_last_rgba()
+    t0 = time.perf_counter()
+    for pk in packets[20:]:
+        state.decode_next_picture(pk)
+        rgba = state.get_last_rgba()
+    sync_s = time.perf_counter() - t0
+    assert rgba.size == W * H * 4
+    # and the CPU port on one core, same packets, planes + RGBA per picture
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+
+    ost = O.OracleState(1)
+    for pk in packets[:20]:
+        ost.decode_next_picture(pk)
+    t0 = time.perf_counter()
+    for pk in packets[20:]:
+        ost.decode_next_picture(pk)
+        y, cb, cr = ost.yuv()
+        O.yuv420_to_rgba(y, cb, cr, W)
+    cpu_s = time.perf_counter() - t0
+    sync_fps, cpu_fps = (n - 20) / sync_s, (n - 20) / cpu_s
     return {"frames_per_s": fps, "value": fps * W * H / 1e6, "unit": UNIT, "pictures": n,
-            "note": "one dependent kernel launch per picture (396 macroblocks): latency bound, not a roofline case"}
+            "note": "one dependent kernel launch per picture (396 macroblocks): latency bound, not a roofline case",
+            "synchronous_api": {"frames_per_s": sync_fps, "value": sync_fps * W * H / 1e6, "unit": UNIT,
+                                "us_per_picture": sync_s / (n - 20) * 1e6,
+                                "path": "H263State.decode_next_picture + get_last_rgba per packet (host parse, H2D, kernel, "
+                                        "D2H of 405 504 bytes, all serial), Python caller"},
+            "cpu_port_one_core": {"frames_per_s": cpu_fps, "value": cpu_fps * W * H / 1e6, "unit": UNIT,
+                                  "note": "oracle (C++ restatement of h263-rs) on one host core, same packets, planes + RGBA"}}
 
 
 def config4_deblock(api, frontend, device, threads, n_streams=256, n_steps=6):

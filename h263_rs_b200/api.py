@@ -216,18 +216,60 @@ class H263State:
         self.ctx = None
         self.out_flags = _lib.OUT_RGBA | (_lib.OUT_DEBLOCK if deblock else 0)
         self._has_picture = False
+        # pinned RGBA of the last picture, and the one-element argument arrays of h263cu_decode_step
+        self._rgba_host, self._rgba_size, self._rgba_view = None, 0, None
+        self._one_parser = (C.c_void_p * 1)(self.parser.h)
+        self._one_packet = (C.c_void_p * 1)()
+        self._one_len = (C.c_size_t * 1)()
+        self._one_id = np.zeros(1, np.uint32)
+        self._one_err = np.zeros(1, np.int32)
 
     def is_sorenson(self):
         return bool(self.decoder_options & SORENSON_SPARK_BITSTREAM)
 
     def decode_next_picture(self, packet):
-        pic, mbs, events = self.parser.parse_picture(bytes(packet))
-        w, h = int(pic["width"][0]), int(pic["height"][0])
+        """One call into h263cu_decode_step for the one stream: parse into the context's pinned staging, upload,
+        reconstruction and the RGBA read-back into this state's pinned buffer, then wait.  Transactional like the
+        reference (state.rs:120-137): a packet that fails to parse raises and leaves parser and stream untouched."""
+        data = bytes(packet)
+        buf = np.frombuffer(data, np.uint8)
+        hdr = frontend.peek_picture(data, self.decoder_options)
+        w, h = int(hdr["width"]), int(hdr["height"])
+        if w == 0 or h == 0:
+            w = h = 16  # no usable size in the header: the parse inside decode_step reports the reference's error
         if self.ctx is None or w > self.ctx.max_width or h > self.ctx.max_height:
             self.ctx = Context(self.device, 1, max(w, 16), max(h, 16))
-        self.ctx.submit_step(pic, mbs, events, self.out_flags)
+            self._has_picture = False
+        L = _lib.lib()
+        size = w * h * 4
+        if size != self._rgba_size:
+            if self._rgba_host:
+                self.ctx.sync()
+                L.h263cu_free_pinned(self._rgba_host)
+            self._rgba_host = L.h263cu_alloc_pinned(size)
+            if not self._rgba_host:
+                self._rgba_size = 0
+                raise MemoryError
+            self._rgba_size = size
+            self._rgba_view = np.ctypeslib.as_array(C.cast(self._rgba_host, C.POINTER(C.c_uint8)), shape=(size,))
+        nd = C.c_uint32(0)
+        self._one_packet[0], self._one_len[0], self._one_err[0] = buf.ctypes.data, buf.size, 0
+        _lib.check(L.h263cu_decode_step(self.ctx.h, self._one_parser, self._one_packet, self._one_len, self._one_id.ctypes.data, 1, 1,
+                                        self.out_flags, self._rgba_host, 0, self._one_err.ctypes.data, C.byref(nd)))
+        if self._one_err[0]:
+            raise _lib.H263Error(int(self._one_err[0]))
         self.ctx.sync()
         self._has_picture = True
+
+    def __del__(self):
+        if getattr(self, "_rgba_host", None):
+            try:
+                if self.ctx is not None:
+                    self.ctx.sync()
+                _lib.lib().h263cu_free_pinned(self._rgba_host)
+            except Exception:
+                pass
+            self._rgba_host = None
 
     def get_last_picture(self):
         if not self._has_picture:
@@ -254,7 +296,7 @@ class H263State:
         """RGBA of the last picture (fused yuv420_to_rgba, or deblock + yuv420_to_rgba)."""
         if not self._has_picture:
             return None
-        return self.ctx.read_rgba(0)
+        return self._rgba_view.copy()  # read back by decode_next_picture; the pinned buffer is reused by the next call
 
 
 class BatchDecoder:
