@@ -74,6 +74,7 @@ SYMBOLS = [
     "h263cu_profile_enable", "h263cu_profile_read",
     "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength", "h263cu_synth_default_params",
     "h263cu_synth_stream", "h263cu_flv_scan", "h263cu_flv_mux",
+    "h263cu_test_read_bits", "h263cu_test_start_code", "h263cu_test_read_vlc", "h263cu_test_decode_block",
 ]
 
 _lib = None
@@ -147,6 +148,11 @@ def lib():
     L.h263cu_flv_scan.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.POINTER(u32)]
     L.h263cu_flv_mux.restype = C.c_int64
     L.h263cu_flv_mux.argtypes = [vp, vp, vp, vp, u32, u32, u32, vp, C.c_size_t]
+    L.h263cu_test_read_bits.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), i32, i32, i32, C.POINTER(C.c_int64)]
+    L.h263cu_test_start_code.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.POINTER(i32)]
+    L.h263cu_test_read_vlc.argtypes = [i32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(i32)]
+    L.h263cu_test_decode_block.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), u32, i32, i32, i32, C.POINTER(i32),
+                                           C.POINTER(i32), vp, vp, C.POINTER(i32)]
     _lib = L
     return L
 

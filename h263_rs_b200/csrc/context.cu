@@ -1,6 +1,6 @@
 // context.cu -- device context, step objects and the device half of the C ABI
 // (include/h263cu.h).  The context owns all device memory: per stream two reconstruction
-// slots (current / reference, ping-pong) for Y, Cb, Cr and a two-deep RGBA ring; side
+// slots (current / reference, ping-pong) for Y and the interleaved CbCr plane and a two-deep RGBA ring; side
 // info arrives through pinned cudaMemcpyAsync.  Everything here is plumbing around the
 // kernels in kernels.cu -- there is no CPU fallback: without a usable device the entry
 // points return H263CU_ERR_NO_DEVICE / H263CU_ERR_CUDA.
@@ -70,7 +70,8 @@ struct h263cu_ctx {
     uint32_t mbw = 0, mbh = 0;
     uint32_t pitch_y = 0, pitch_c = 0, rgba_pitch = 0;
     size_t y_slot = 0, c_slot = 0, rgba_slot = 0;
-    uint8_t *y_pool = nullptr, *cb_pool = nullptr, *cr_pool = nullptr, *rgba_pool = nullptr;
+    uint8_t *y_pool = nullptr, *c_pool = nullptr, *rgba_pool = nullptr;  // c_pool: interleaved CbCr planes
+    CUtensorMap rgba_map;  // TMA view of rgba_pool: rows of rgba_pitch bytes, box 64 bytes x 16 rows (one macroblock)
     std::vector<StreamState> streams;
     uint32_t stamp = 0, decode_epoch = 0;
     uint32_t rgba_parity = 0;
@@ -112,7 +113,6 @@ struct h263cu_ctx {
     };
     std::vector<ProfSpan> prof_spans;
     // checksum scratch
-    uint32_t* d_work_counter = nullptr;  // tile counter of the persistent recon kernel
     ChecksumJob* d_jobs = nullptr;
     unsigned long long* d_sums = nullptr;
     size_t jobs_cap = 0;
@@ -122,7 +122,8 @@ struct h263cu_ctx {
     uint8_t* plane(int p, uint32_t stream, int slot) const {
         const size_t idx = (size_t)stream * 2 + (size_t)slot;
         if (p == 0) return y_pool + idx * y_slot + (size_t)PAD_Y_ROWS * pitch_y + PAD_Y_COLS;
-        return (p == 1 ? cb_pool : cr_pool) + idx * c_slot + (size_t)PAD_C_ROWS * pitch_c + PAD_C_COLS;
+        // Cb and Cr share one interleaved plane: Cr starts one byte after Cb, samples are CHROMA_STEP bytes apart
+        return c_pool + idx * c_slot + (size_t)PAD_C_ROWS * pitch_c + PAD_C_COLS + (p == 2 ? 1 : 0);
     }
     uint8_t* rgba(uint32_t stream, int slot) const { return rgba_pool + ((size_t)slot * max_streams + stream) * rgba_slot; }
 };
@@ -236,10 +237,10 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         }
         d.rgba = want_rgba ? c->rgba(p.stream, rgba_ring) : nullptr;
         d.cur_y4 = (uint32_t)((d.cur[0] - c->y_pool) >> 2);
-        d.cur_c4 = (uint32_t)((d.cur[1] - c->cb_pool) >> 2);
+        d.cur_c4 = (uint32_t)((d.cur[1] - c->c_pool) >> 2);
         d.ref_y4 = st.has_pic ? (uint32_t)((d.ref[0] - c->y_pool) >> 2) : 0u;
-        d.ref_c4 = st.has_pic ? (uint32_t)((d.ref[1] - c->cb_pool) >> 2) : 0u;
-        d.rgba16 = want_rgba ? (uint32_t)((d.rgba - c->rgba_pool) >> 4) : 0u;
+        d.ref_c4 = st.has_pic ? (uint32_t)((d.ref[1] - c->c_pool) >> 2) : 0u;
+        d.rgba_row0 = want_rgba ? (uint32_t)((size_t)(d.rgba - c->rgba_pool) / c->rgba_pitch) : 0u;
         d.first_event = p.first_event;
         d.rgba_pitch = c->rgba_pitch;
         d.w = p.width, d.h = p.height;
@@ -267,9 +268,9 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     }
     cudaEvent_t pa = nullptr, pb = nullptr;
     if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
-    const Pools pools{c->y_pool, c->cb_pool, c->cr_pool, c->rgba_pool, c->d_work_counter, c->pitch_y, c->pitch_c, c->rgba_pitch};
+    const Pools pools{c->y_pool, c->c_pool, c->rgba_pool, c->pitch_y, c->pitch_c, c->rgba_pitch};
     launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? (aligned16 ? 1 : 2) : 0, wide_mv, pools,
-                 c->s_main);
+                 &c->rgba_map, c->s_main);
     c->launches++;
     if (tiled) c->tiled_launches++;
     if (c->profiling) prof_end(c, pa, pb, 0);
@@ -312,6 +313,27 @@ int grow_pinned(T** p, size_t* cap, size_t need) {
     const size_t n = need + need / 4 + 64;
     CU_TRY(cudaHostAlloc((void**)p, n * sizeof(T), cudaHostAllocDefault));
     *cap = n;
+    return 0;
+}
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+int make_rgba_map(CUtensorMap* map, void* base, uint64_t pitch, uint64_t rows) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    std::memset(map, 0, sizeof(*map));
+    if (!recon_tile_uses_tma()) return 0;
+    EncodeTiled enc = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&enc, cudaEnableDefault, &q) != cudaSuccess || !enc) {
+        cudaGetLastError();
+        return H263CU_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {pitch, rows}, strides[1] = {pitch};
+    const cuuint32_t box[2] = {64, 16}, es[2] = {1, 1};
+    const CUtensorMapSwizzle sw = recon_tile_uses_tma() == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B;
+    if (enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return H263CU_ERR_CUDA;
     return 0;
 }
 void free_step_buffers(h263cu_step* s) {
@@ -372,7 +394,7 @@ h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, 
     // plus a border (PAD_*) into which the tiled kernel replicates the edge pixels, so that
     // motion compensation needs no per-sample clamping (unrestricted-MV extension)
     c->pitch_y = c->mbw * 16 + 2 * PAD_Y_COLS;
-    c->pitch_c = (uint32_t)round_up(c->mbw * 8 + 2 * PAD_C_COLS, 16);
+    c->pitch_c = c->mbw * 8 * CHROMA_STEP + 2 * PAD_C_COLS;  // interleaved CbCr rows: the same pitch as luma
     c->rgba_pitch = c->mbw * 16 * 4;
     c->y_slot = (size_t)c->pitch_y * (c->mbh * 16 + 2 * PAD_Y_ROWS);
     c->c_slot = (size_t)c->pitch_c * (c->mbh * 8 + 2 * PAD_C_ROWS);
@@ -389,10 +411,14 @@ h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, 
     // 16-byte units for RGBA
     if (c->y_slot * 2 * max_streams + pad >= (16ull << 30) || c->rgba_slot * 2 * max_streams + pad >= (64ull << 30)) return fail(H263CU_ERR_CAPACITY);
     if (cudaMalloc((void**)&c->y_pool, c->y_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
-    if (cudaMalloc((void**)&c->cb_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
-    if (cudaMalloc((void**)&c->cr_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc((void**)&c->c_pool, c->c_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
     if (cudaMalloc((void**)&c->rgba_pool, c->rgba_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
-    if (cudaMalloc((void**)&c->d_work_counter, 256) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
+    {
+        // TMA tensor map over the RGBA pool: the reconstruction kernel stores one 64-byte x 16-row box per macroblock
+        // (cp.async.bulk.tensor.2d) from a 128B-swizzled shared-memory tile
+        const int e = make_rgba_map(&c->rgba_map, c->rgba_pool, c->rgba_pitch, (uint64_t)2 * max_streams * c->mbh * 16);
+        if (e) return fail(e);
+    }
     if (cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail(H263CU_ERR_CUDA);
@@ -412,8 +438,7 @@ h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, 
     // planes start out zeroed (DecodedPicture::new, picture.rs:39-58); every macroblock of a
     // picture is rewritten by the kernel, so this only matters for defensive reads
     cudaMemsetAsync(c->y_pool, 0, c->y_slot * 2 * max_streams + pad, c->s_main);
-    cudaMemsetAsync(c->cb_pool, 0, c->c_slot * 2 * max_streams + pad, c->s_main);
-    cudaMemsetAsync(c->cr_pool, 0, c->c_slot * 2 * max_streams + pad, c->s_main);
+    cudaMemsetAsync(c->c_pool, 0, c->c_slot * 2 * max_streams + pad, c->s_main);
     if (cudaStreamSynchronize(c->s_main) != cudaSuccess) return fail(H263CU_ERR_CUDA);
     return c;
 }
@@ -452,10 +477,8 @@ void h263cu_destroy(h263cu_ctx* c) {
     for (auto e : c->prof_free) cudaEventDestroy(e);
     if (c->d_jobs) cudaFree(c->d_jobs);
     if (c->d_sums) cudaFree(c->d_sums);
-    if (c->d_work_counter) cudaFree(c->d_work_counter);
     if (c->y_pool) cudaFree(c->y_pool);
-    if (c->cb_pool) cudaFree(c->cb_pool);
-    if (c->cr_pool) cudaFree(c->cr_pool);
+    if (c->c_pool) cudaFree(c->c_pool);
     if (c->rgba_pool) cudaFree(c->rgba_pool);
     if (c->s_main) cudaStreamDestroy(c->s_main);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -661,8 +684,16 @@ int h263cu_read_yuv(h263cu_ctx* c, uint32_t stream, uint8_t* y, uint8_t* cb, uin
     CU_TRY(cudaStreamSynchronize(c->s_main));
     const size_t cw = (st.w + 1) / 2, ch = (st.h + 1) / 2;
     CU_TRY(cudaMemcpy2D(y, st.w, c->plane(0, stream, st.cur_slot), c->pitch_y, st.w, st.h, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy2D(cb, cw, c->plane(1, stream, st.cur_slot), c->pitch_c, cw, ch, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy2D(cr, cw, c->plane(2, stream, st.cur_slot), c->pitch_c, cw, ch, cudaMemcpyDeviceToHost));
+    // the chroma planes live interleaved on the device: copy the CbCr rows and split them here
+    std::vector<uint8_t> pairs;
+    try {
+        pairs.resize(cw * ch * CHROMA_STEP);
+    } catch (const std::bad_alloc&) {
+        return H263CU_ERR_OUT_OF_MEMORY;
+    }
+    CU_TRY(cudaMemcpy2D(pairs.data(), cw * CHROMA_STEP, c->plane(1, stream, st.cur_slot), c->pitch_c, cw * CHROMA_STEP, ch,
+                        cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < cw * ch; i++) cb[i] = pairs[2 * i], cr[i] = pairs[2 * i + 1];
     return 0;
 }
 
@@ -688,11 +719,11 @@ int h263cu_checksums(h263cu_ctx* c, const uint32_t* streams, uint32_t n, uint64_
         const StreamState& st = c->streams[streams[i]];
         if (!st.has_pic) return H263CU_ERR_NO_PICTURE;
         const uint32_t cw = (st.w + 1u) / 2u, ch = (st.h + 1u) / 2u;
-        jobs.push_back({c->plane(0, streams[i], st.cur_slot), st.w, st.h, c->pitch_y, i * 4 + 0});
-        jobs.push_back({c->plane(1, streams[i], st.cur_slot), cw, ch, c->pitch_c, i * 4 + 1});
-        jobs.push_back({c->plane(2, streams[i], st.cur_slot), cw, ch, c->pitch_c, i * 4 + 2});
+        jobs.push_back({c->plane(0, streams[i], st.cur_slot), st.w, st.h, c->pitch_y, i * 4 + 0, 1u, 0u});
+        jobs.push_back({c->plane(1, streams[i], st.cur_slot), cw, ch, c->pitch_c, i * 4 + 1, (uint32_t)CHROMA_STEP, 0u});
+        jobs.push_back({c->plane(2, streams[i], st.cur_slot), cw, ch, c->pitch_c, i * 4 + 2, (uint32_t)CHROMA_STEP, 0u});
         if (st.rgba_slot >= 0)
-            jobs.push_back({c->rgba(streams[i], st.rgba_slot), (uint32_t)st.w * 4u, st.h, c->rgba_pitch, i * 4 + 3});
+            jobs.push_back({c->rgba(streams[i], st.rgba_slot), (uint32_t)st.w * 4u, st.h, c->rgba_pitch, i * 4 + 3, 1u, 0u});
     }
     if (jobs.size() > c->jobs_cap) {
         if (c->d_jobs) cudaFree(c->d_jobs);

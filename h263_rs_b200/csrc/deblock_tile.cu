@@ -132,16 +132,18 @@ __global__ void __launch_bounds__(DB_THREADS) deblock_rgba_tile_kernel(const Pic
         const int cx0 = 8 * M - 2 + 4 * a, cy0 = 8 * N - 2 + 4 * b;  // = x0 / 2, y0 / 2
         const bool do_h = b == 0 && 8 * N >= 8 && 8 * N <= CH - 2;              // chroma edge row 8N: quadrant rows 0..3
         const bool do_v = a == 0 && CW >= 10 && 8 * M >= 8 && 8 * M + 2 <= CW;  // chroma edge column 8M: columns 0..3
+        // the planes are interleaved (CbCr pairs): samples cx0..cx0+3 of both planes are the 8 bytes at 2 * cx0,
+        // which is a multiple of 4: two aligned words per row serve both planes
+        const uint8_t* src = P.cur[1] + (ptrdiff_t)cy0 * pitch_c + (ptrdiff_t)cx0 * CHROMA_STEP;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(src + j * pitch_c));      // cb0 cr0 cb1 cr1
+            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(src + j * pitch_c + 4));  // cb2 cr2 cb3 cr3
+            ce[0][j] = __byte_perm(w0, w1, 0x0400) & 0x00FF00FFu, co[0][j] = __byte_perm(w0, w1, 0x0602) & 0x00FF00FFu;
+            ce[1][j] = __byte_perm(w0, w1, 0x0501) & 0x00FF00FFu, co[1][j] = __byte_perm(w0, w1, 0x0703) & 0x00FF00FFu;
+        }
 #pragma unroll
         for (int pl = 0; pl < 2; pl++) {
-            const uint8_t* src = P.cur[1 + pl] + (ptrdiff_t)cy0 * pitch_c + (cx0 - 2);  // 4-byte aligned
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(src + j * pitch_c));
-                const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(src + j * pitch_c + 4));
-                const uint32_t w = __byte_perm(w0, w1, 0x5432);  // the four samples start 2 bytes into w0
-                ce[pl][j] = __byte_perm(w, 0, 0x4240), co[pl][j] = __byte_perm(w, 0, 0x4341);
-            }
             if (do_h) {
                 deblock2(ce[pl][0], ce[pl][1], ce[pl][2], ce[pl][3], s2);
                 deblock2(co[pl][0], co[pl][1], co[pl][2], co[pl][3], s2);

@@ -808,6 +808,70 @@ int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packe
     return 0;
 }
 
+// ---- test hooks: the front end's own bit reader, tables and block decoder behind plain C calls, so that the
+// reference's parser known-answer tests (reader.rs:448-559, macroblock.rs:551-1010, block.rs:757-2124) are replayed
+// on the PRODUCT code and not only on the oracle (tests/test_frontend_kats.py).  Not on any decode path.
+int h263cu_test_read_bits(const uint8_t* data, size_t len, size_t* bitpos, int nbits, int is_signed, int peek, int64_t* value) {
+    if (!data || !bitpos || !value || nbits < 0 || nbits > 32) return H263CU_ERR_BAD_ARGUMENT;
+    BitReader r(data, len);
+    if (*bitpos > len * 8) return H263CU_ERR_BAD_ARGUMENT;
+    r.seek(*bitpos);
+    if (nbits == 0) {
+        *value = 0;
+        return 0;
+    }
+    if (is_signed) {
+        int32_t v;
+        if (!r.read_signed((unsigned)nbits, &v)) return H263CU_ERR_UNHANDLED_IO_ERROR;
+        *value = v;
+    } else {
+        uint32_t v;
+        if (!r.read((unsigned)nbits, &v)) return H263CU_ERR_UNHANDLED_IO_ERROR;
+        *value = v;
+    }
+    if (!peek) *bitpos = r.pos();
+    return 0;
+}
+
+int h263cu_test_start_code(const uint8_t* data, size_t len, size_t bitpos, int* skipped) {
+    if (!data || !skipped || bitpos > len * 8) return H263CU_ERR_BAD_ARGUMENT;
+    BitReader r(data, len);
+    r.seek(bitpos);
+    uint32_t sk = 0;
+    const int e = find_start_code(r, &sk);
+    *skipped = e ? -1 : (int)sk;
+    return e;
+}
+
+int h263cu_test_read_vlc(int table, const uint8_t* data, size_t len, size_t* bitpos, int* out4) {
+    if (table < 0 || table > 4 || !data || !bitpos || !out4 || *bitpos > len * 8) return H263CU_ERR_BAD_ARGUMENT;
+    BitReader r(data, len);
+    r.seek(*bitpos);
+    const VlcEntry* e;
+    if (!r.read_vlc(vlc_table(table), &e)) return H263CU_ERR_UNHANDLED_IO_ERROR;
+    *bitpos = r.pos();
+    out4[0] = (int)e->kind(), out4[1] = e->a, out4[2] = e->b, out4[3] = e->c;
+    return 0;
+}
+
+int h263cu_test_decode_block(const uint8_t* data, size_t len, size_t* bitpos, uint32_t decoder_options, int version, int is_intra,
+                             int tcoef_present, int* intradc_code, int* n_events, uint8_t* run, int16_t* level, int* overflow) {
+    if (!data || !bitpos || !intradc_code || !n_events || !run || !level || *bitpos > len * 8) return H263CU_ERR_BAD_ARGUMENT;
+    BitReader r(data, len);
+    r.seek(*bitpos);
+    Header hd;
+    hd.version = version;
+    uint8_t ev_run[64];
+    int16_t ev_level[64];
+    bool ovf = false;
+    const int e = parse_block(r, hd, decoder_options, is_intra != 0, tcoef_present != 0, intradc_code, ev_run, ev_level, n_events, &ovf);
+    if (e) return e;
+    for (int k = 0; k < *n_events; k++) run[k] = ev_run[k], level[k] = ev_level[k];
+    if (overflow) *overflow = ovf;
+    *bitpos = r.pos();
+    return 0;
+}
+
 int h263cu_is_eof_error(int err) { return err == H263CU_ERR_UNHANDLED_IO_ERROR; }
 int h263cu_is_macroblock_error(int err) {
     return err == H263CU_ERR_INVALID_MACROBLOCK_HEADER || err == H263CU_ERR_INVALID_MACROBLOCK_CODED_BITS;

@@ -244,16 +244,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
         *reinterpret_cast<uint2*>(&S.rec[rowpix * 16 + half * 8]) = make_uint2(p0, p1);
     }
     if (lane < 16) {
-        // chroma: lane -> plane (lane >> 3), row (lane & 7); both planes share one vector
+        // chroma: lane -> plane (lane >> 3), row (lane & 7); both planes share one vector.  The planes are
+        // interleaved (CbCr pairs): samples of one plane are CHROMA_STEP bytes apart.
         const int plane = lane >> 3, j = lane & 7, b = 4 + plane;
         const int c = plane ? cls[5] : cls[4];
         const int dcv = plane ? dcres[5] : dcres[4];
-        uint32_t p0 = 0, p1 = 0;
+        uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (inter && P.ref[1 + plane]) {
             const int cx = average_sum_of_mvs(mv0x + mv1x + mv2x + mv3x);
             const int cy = average_sum_of_mvs(mv0y + mv1y + mv2y + mv3y);
-            mc_fetch8(P.ref[1 + plane], P.pitch_c, P.cw, P.ch, mbx * 8, mby * 8 + j, cx, cy, p0, p1);
+#pragma unroll
+            for (int k = 0; k < 8; k++) px[k] = mc_fetch1(P.ref[1 + plane], P.pitch_c, CHROMA_STEP, P.cw, P.ch, mbx * 8 + k, mby * 8 + j, cx, cy);
         }
+        uint32_t p0 = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24), p1 = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
         if (c == CLS_DC) {
             p0 = add_clamp4(p0, dcv, dcv, dcv, dcv);
             p1 = add_clamp4(p1, dcv, dcv, dcv, dcv);
@@ -262,7 +265,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
             p0 = add_clamp4(p0, (int16_t)(rv.x & 0xFFFF), rv.x >> 16, (int16_t)(rv.y & 0xFFFF), rv.y >> 16);
             p1 = add_clamp4(p1, (int16_t)(rv.z & 0xFFFF), rv.z >> 16, (int16_t)(rv.w & 0xFFFF), rv.w >> 16);
         }
-        *reinterpret_cast<uint2*>(P.cur[1 + plane] + (size_t)(mby * 8 + j) * P.pitch_c + mbx * 8) = make_uint2(p0, p1);
+        uint8_t* dst = P.cur[1 + plane] + (size_t)(mby * 8 + j) * P.pitch_c + (size_t)(mbx * 8) * CHROMA_STEP;
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k * CHROMA_STEP] = (uint8_t)byte_of(p0, k), dst[(k + 4) * CHROMA_STEP] = (uint8_t)byte_of(p1, k);
         *reinterpret_cast<uint2*>(&S.rec[256 + plane * 64 + j * 8]) = make_uint2(p0, p1);
     }
 
@@ -288,10 +293,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 }
 
 void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs, int emit_rgba,
-                  int tiled, int wide_mv, const Pools& pools, cudaStream_t stream) {
+                  int tiled, int wide_mv, const Pools& pools, const CUtensorMap* rgba_map, cudaStream_t stream) {
     if (n_mbs == 0) return;
     if (tiled) {
-        launch_recon_tile(pics, mbs, events, n_mbs, emit_rgba, tiled == 2, wide_mv, pools, stream);
+        launch_recon_tile(pics, mbs, events, n_mbs, emit_rgba, tiled == 2, wide_mv, pools, rgba_map, stream);
     } else {
         const uint32_t grid = (n_mbs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         recon_mb_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba);
@@ -307,13 +312,13 @@ void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* 
 //   Horizontal edges first over the whole plane, then vertical edges (deblock.rs:305-315).
 // =======================================================================================
 template <int TW, int TH, int RS, int CO>
-__device__ __forceinline__ void deblock_tile(uint8_t* sm, const uint8_t* __restrict__ src, int pitch, int W, int H,
+__device__ __forceinline__ void deblock_tile(uint8_t* sm, const uint8_t* __restrict__ src, int pitch, int step, int W, int H,
                                              int ox, int oy, int strength, int tid, int nthreads) {
     constexpr int RW = TW + 4, RH = TH + 4;
     for (int idx = tid; idx < RW * RH; idx += nthreads) {
         const int rx = idx % RW, ry = idx / RW;
         const int gx = min(max(ox - 2 + rx, 0), W - 1), gy = min(max(oy - 2 + ry, 0), H - 1);
-        sm[ry * RS + CO + rx] = src[(size_t)gy * pitch + gx];
+        sm[ry * RS + CO + rx] = src[(size_t)gy * pitch + (size_t)gx * step];
     }
     __syncthreads();
     // horizontal edges: rows ey-2 .. ey+1 for ey = 8, 16, ... <= H - 2 (deblock.rs:136-181);
@@ -358,9 +363,9 @@ __global__ void __launch_bounds__(256) deblock_rgba_kernel(const PicDev* __restr
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     const int tid = threadIdx.x;
     const int strength = P.strength;
-    deblock_tile<32, 32, 40, 2>(sy, P.cur[0], P.pitch_y, W, H, tx * 32, ty * 32, strength, tid, 256);
-    deblock_tile<16, 16, 24, 2>(scb, P.cur[1], P.pitch_c, P.cw, P.ch, tx * 16, ty * 16, strength, tid, 256);
-    deblock_tile<16, 16, 24, 2>(scr, P.cur[2], P.pitch_c, P.cw, P.ch, tx * 16, ty * 16, strength, tid, 256);
+    deblock_tile<32, 32, 40, 2>(sy, P.cur[0], P.pitch_y, 1, W, H, tx * 32, ty * 32, strength, tid, 256);
+    deblock_tile<16, 16, 24, 2>(scb, P.cur[1], P.pitch_c, CHROMA_STEP, P.cw, P.ch, tx * 16, ty * 16, strength, tid, 256);
+    deblock_tile<16, 16, 24, 2>(scr, P.cur[2], P.pitch_c, CHROMA_STEP, P.cw, P.ch, tx * 16, ty * 16, strength, tid, 256);
     if (!P.rgba) return;
     const int row = tid >> 3, xq = tid & 7;
     const int gx = tx * 32 + xq * 4, gy = ty * 32 + row;
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(256)
     __shared__ __align__(16) uint8_t sm[36 * 40];
     const int tiles_x = (W + 31) >> 5;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    deblock_tile<32, 32, 40, 2>(sm, in, W, W, H, tx * 32, ty * 32, strength, threadIdx.x, 256);
+    deblock_tile<32, 32, 40, 2>(sm, in, W, 1, W, H, tx * 32, ty * 32, strength, threadIdx.x, 256);
     for (int idx = threadIdx.x; idx < 32 * 32; idx += 256) {
         const int rx = idx & 31, ry = idx >> 5;
         const int gx = tx * 32 + rx, gy = ty * 32 + ry;
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(256) checksum_kernel(const ChecksumJob* __rest
     unsigned long long s = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t x = (uint32_t)(i % J.row_bytes), yy = (uint32_t)(i / J.row_bytes);
-        const uint32_t v = J.base[(size_t)yy * J.pitch + x];
+        const uint32_t v = J.base[(size_t)yy * J.pitch + (size_t)x * J.step];
         s += (unsigned long long)(v + 1u) * (unsigned long long)(((uint32_t)i * 2654435761u) | 1u);
     }
 #pragma unroll

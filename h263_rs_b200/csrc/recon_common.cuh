@@ -104,6 +104,24 @@ __device__ __forceinline__ void mc_fetch8(const uint8_t* __restrict__ ref, int p
     }
 }
 
+// One prediction sample of a plane whose samples are `step` bytes apart, through read_sample's clamp
+// (gather.rs:16-31) and lerp (gather.rs:34-40, 103-113).
+__device__ __forceinline__ uint32_t mc_fetch1(const uint8_t* __restrict__ ref, int pitch, int step, int W, int H, int x, int y,
+                                              int mvx, int mvy) {
+    const int sx = x + (mvx >> 1), sy = y + (mvy >> 1), ix = mvx & 1, iy = mvy & 1;
+    const int x0 = min(max(sx, 0), W - 1), x1 = min(max(sx + 1, 0), W - 1);
+    const int y0 = min(max(sy, 0), H - 1), y1 = min(max(sy + 1, 0), H - 1);
+    const uint32_t a = ref[(size_t)y0 * pitch + x0 * step];
+    if (ix && iy) {
+        const uint32_t b = ref[(size_t)y0 * pitch + x1 * step], c = ref[(size_t)y1 * pitch + x0 * step],
+                       d = ref[(size_t)y1 * pitch + x1 * step];
+        return (a + b + c + d + 2u) >> 2;
+    }
+    if (ix) return (a + ref[(size_t)y0 * pitch + x1 * step] + 1u) >> 1;
+    if (iy) return (a + ref[(size_t)y1 * pitch + x0 * step] + 1u) >> 1;
+    return a;
+}
+
 __device__ __forceinline__ void load_event(const h263cu_event* __restrict__ ev, uint32_t idx, bool wide, int& run,
                                            int& level) {
     if (wide) {

@@ -173,6 +173,20 @@ int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packe
                       uint32_t* n_pics_out, uint32_t* n_mbs_out, uint32_t* n_units_out,
                       int* per_pic_err, int32_t* pic_of_input);
 
+/* ---- test hooks: the front end's bit reader, VLC tables and block decoder as plain calls, so that the
+ *      reference's own parser known-answer tests (reader.rs:448-559, macroblock.rs:551-1010, block.rs:757-2124)
+ *      can be replayed on the product code.  Tables: 0 MCBPC_I, 1 MCBPC_P, 2 CBPY, 3 MVD, 4 TCOEF;
+ *      out4 = {kind (0 valid, 1 stuffing, 2 invalid, 3 escape), a, b, c} as in csrc/vlc_codes.inc. ---- */
+int h263cu_test_read_bits(const uint8_t* data, size_t len, size_t* bitpos, int nbits, int is_signed, int peek,
+                          int64_t* value);
+/* recognize_start_code (reader.rs:240-258): *skipped = stuffing bits before the code, -1 when there is none */
+int h263cu_test_start_code(const uint8_t* data, size_t len, size_t bitpos, int* skipped);
+int h263cu_test_read_vlc(int table, const uint8_t* data, size_t len, size_t* bitpos, int* out4);
+/* decode_block (block.rs:670-755): *intradc_code = -1 when absent; run/level hold up to 64 events */
+int h263cu_test_decode_block(const uint8_t* data, size_t len, size_t* bitpos, uint32_t decoder_options, int version,
+                             int is_intra, int tcoef_present, int* intradc_code, int* n_events, uint8_t* run,
+                             int16_t* level, int* overflow);
+
 /* ---- device context ---------------------------------------------------------------- */
 typedef struct h263cu_ctx h263cu_ctx;
 typedef struct h263cu_step h263cu_step;

@@ -98,3 +98,45 @@ def compare_parse_with_oracle(packets, options=1):
                 nev += ne
         nmb += len(mbs)
     return nmb, nev, nerr
+
+
+def recon_from_side_info(pic, mbs, events, ref=None):
+    """The reference's reconstruction tail (state.rs:419-485) on one picture's side info, put together from the
+    oracle's exported pieces: gather_block (gather.rs:47-126) per inter block with the chroma vector of
+    gather.rs:182, then inverse_rle (rle.rs:82-172) + idct_channel on one block (idct.rs:82-201).  Works on
+    hand-built records, so it checks what no bitstream can reach (vectors beyond the parser's range, escape levels
+    at the i16-wrap boundary).  Picture sizes must be multiples of 16.  `ref` = (y, cb, cr) planes or None.
+    Returns (y, cb, cr) as 2-D arrays."""
+    w, h = int(pic["width"]), int(pic["height"])
+    assert w % 16 == 0 and h % 16 == 0
+    cw, ch = w // 2, h // 2
+    planes = [np.zeros((h, w), np.uint8), np.zeros((ch, cw), np.uint8), np.zeros((ch, cw), np.uint8)]
+    L = O.lib()
+    for m in mbs:
+        mbx, mby = int(m["mbx"]), int(m["mby"])
+        inter = bool(m["flags"] & _lib.MB_INTER)
+        if inter:
+            assert ref is not None
+            mv = m["u"].view(np.int8).reshape(4, 2).astype(int)
+            for b in range(4):
+                planes[0] = O.gather_block(np.asarray(ref[0]).reshape(h, w), (mbx * 16 + (b & 1) * 8, mby * 16 + (b >> 1) * 8),
+                                           (int(mv[b][0]), int(mv[b][1])), planes[0])
+            cmv = (L.orc_average_sum_of_mvs(int(mv[:, 0].sum())), L.orc_average_sum_of_mvs(int(mv[:, 1].sum())))
+            for p in (1, 2):
+                planes[p] = O.gather_block(np.asarray(ref[p]).reshape(ch, cw), (mbx * 8, mby * 8), cmv, planes[p])
+        blocks = frontend.decode_events(m, events, int(pic["first_event"]))
+        for b in range(6):
+            dc = None
+            if not inter:
+                dc = int(m["u"][b])
+                if dc == 0:
+                    continue  # dropped block (zig-zag overflow): stays Zero, rle.rs:125-127
+            runs = [r for r, _ in blocks[b]]
+            levels = [l for _, l in blocks[b]]
+            cls, coefs = O.inverse_rle(dc, runs, levels, int(m["quant"]))
+            if b < 4:
+                pl, x0, y0 = planes[0], mbx * 16 + (b & 1) * 8, mby * 16 + (b >> 1) * 8
+            else:
+                pl, x0, y0 = planes[b - 3], mbx * 8, mby * 8
+            pl[y0 : y0 + 8, x0 : x0 + 8] = O.idct_block(cls, coefs, pl[y0 : y0 + 8, x0 : x0 + 8])
+    return planes
