@@ -48,18 +48,6 @@ class Mb(C.Structure):
     ]
 
 
-class SynthParams(C.Structure):
-    _fields_ = [
-        ("width", C.c_uint32), ("height", C.c_uint32), ("n_pictures", C.c_uint32), ("seed", C.c_uint64),
-        ("flavour", C.c_uint32), ("version", C.c_uint32), ("intra_period", C.c_uint32), ("deblock_flag", C.c_uint32),
-        ("qp_min", C.c_uint32), ("qp_max", C.c_uint32), ("pct_uncoded", C.c_uint32), ("pct_intra", C.c_uint32),
-        ("pct_fourmv", C.c_uint32), ("pct_dquant", C.c_uint32), ("pct_cbp_inter", C.c_uint32),
-        ("pct_cbp_intra", C.c_uint32), ("mean_events_x10", C.c_uint32), ("pct_escape", C.c_uint32),
-        ("permille_overflow", C.c_uint32), ("mv_mode", C.c_uint32), ("truncate_permille", C.c_uint32),
-        ("reserved", C.c_uint32 * 4),
-    ]
-
-
 assert C.sizeof(Pic) == 32 and C.sizeof(Mb) == 24
 
 # Every symbol include/h263cu.h declares; tests check that the library exports all of them.
@@ -72,9 +60,11 @@ SYMBOLS = [
     "h263cu_submit_step_readback", "h263cu_decode_step", "h263cu_sync", "h263cu_stream_info", "h263cu_read_yuv", "h263cu_read_rgba",
     "h263cu_checksums", "h263cu_timer_start", "h263cu_timer_stop", "h263cu_launch_count", "h263cu_tiled_launch_count",
     "h263cu_profile_enable", "h263cu_profile_read",
-    "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength", "h263cu_synth_default_params",
-    "h263cu_synth_stream", "h263cu_flv_scan", "h263cu_flv_mux",
+    "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength",
+    "h263cu_flv_scan", "h263cu_flv_mux",
     "h263cu_test_read_bits", "h263cu_test_start_code", "h263cu_test_read_vlc", "h263cu_test_decode_block",
+    "h263cu_readback_wait", "h263cu_group_create", "h263cu_group_destroy", "h263cu_group_size", "h263cu_group_ctx",
+    "h263cu_group_decode_step", "h263cu_group_sync",
 ]
 
 _lib = None
@@ -126,6 +116,17 @@ def lib():
         L.h263cu_submit_step_readback.argtypes = [vp, vp, u32, vp, u32, vp, u32, u32, vp, vp]
         L.h263cu_decode_step.argtypes = [vp, vp, vp, vp, vp, u32, i32, u32, vp, u64, vp, C.POINTER(u32)]
         L.h263cu_sync.argtypes = [vp]
+        L.h263cu_readback_wait.argtypes = [vp, u32]
+        L.h263cu_group_create.restype = vp
+        L.h263cu_group_create.argtypes = [vp, u32, u32, u32, u32, i32, C.POINTER(i32)]
+        L.h263cu_group_destroy.argtypes = [vp]
+        L.h263cu_group_destroy.restype = None
+        L.h263cu_group_size.restype = u32
+        L.h263cu_group_size.argtypes = [vp]
+        L.h263cu_group_ctx.restype = vp
+        L.h263cu_group_ctx.argtypes = [vp, u32]
+        L.h263cu_group_decode_step.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, u64, vp, C.POINTER(u32)]
+        L.h263cu_group_sync.argtypes = [vp]
         L.h263cu_stream_info.argtypes = [vp, u32] + [C.POINTER(u32)] * 5
         L.h263cu_read_yuv.argtypes = [vp, u32, vp, vp, vp]
         L.h263cu_read_rgba.argtypes = [vp, u32, vp]
@@ -140,10 +141,6 @@ def lib():
         L.h263cu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
         L.h263cu_yuv420_to_rgba.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, vp]
         L.h263cu_deblock.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_uint8, vp]
-    L.h263cu_synth_default_params.argtypes = [C.POINTER(SynthParams), u32, u32, u32, u64]
-    L.h263cu_synth_default_params.restype = None
-    L.h263cu_synth_stream.restype = C.c_int64
-    L.h263cu_synth_stream.argtypes = [C.POINTER(SynthParams), vp, C.c_size_t, vp, vp]
     L.h263cu_flv_scan.restype = C.c_int64
     L.h263cu_flv_scan.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.POINTER(u32)]
     L.h263cu_flv_mux.restype = C.c_int64

@@ -114,18 +114,26 @@ class DecodedPicture:
 class Context:
     """Thin RAII wrapper of h263cu_ctx."""
 
-    def __init__(self, device, max_streams, max_width, max_height):
+    def __init__(self, device, max_streams, max_width, max_height, _borrowed=None):
         self.L = _lib.lib()
-        err = C.c_int(0)
-        self.h = self.L.h263cu_create(device, max_streams, max_width, max_height, 0, C.byref(err))
-        if not self.h:
-            raise H263Error(err.value)
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            err = C.c_int(0)
+            self.h = self.L.h263cu_create(device, max_streams, max_width, max_height, 0, C.byref(err))
+            if not self.h:
+                raise H263Error(err.value)
+        else:
+            self.h = _borrowed  # a context that belongs to a DeviceGroup
         self.max_streams, self.max_width, self.max_height = max_streams, max_width, max_height
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.h263cu_destroy(self.h)
+            if self._owned:
+                self.L.h263cu_destroy(self.h)
             self.h = None
+
+    def readback_wait(self, age=0):
+        check(self.L.h263cu_readback_wait(self.h, age))
 
     def __del__(self):
         self.close()
@@ -209,15 +217,20 @@ class H263State:
     through `H263Reader::from_source(&packet[..])`; Sorenson pictures end at EOF, so one
     reader per packet is the only usable form)."""
 
-    def __init__(self, decoder_options=SORENSON_SPARK_BITSTREAM, device=0, deblock=False):
+    def __init__(self, decoder_options=SORENSON_SPARK_BITSTREAM, device=0, deblock=False, pipelined=False):
+        """pipelined=True: decode_next_picture returns as soon as the picture is queued (parse done, upload + kernels +
+        RGBA read-back in flight); get_last_rgba / get_last_picture wait for it.  A caller that hands in packet t + 1
+        before it consumes picture t overlaps the host parse with the device work (two pinned RGBA buffers alternate)."""
         self.decoder_options = decoder_options
         self.device = device
+        self.pipelined = pipelined
+        self._ring, self._ring_size, self._ring_pos, self._pending = [None, None], 0, 0, False
         self.parser = frontend.Parser(decoder_options)
         self.ctx = None
         self.out_flags = _lib.OUT_RGBA | (_lib.OUT_DEBLOCK if deblock else 0)
         self._has_picture = False
-        # pinned RGBA of the last picture, and the one-element argument arrays of h263cu_decode_step
-        self._rgba_host, self._rgba_size, self._rgba_view = None, 0, None
+        # the one-element argument arrays of h263cu_decode_step; the pinned RGBA ring is self._ring
+        self._rgba_view = None
         self._one_parser = (C.c_void_p * 1)(self.parser.h)
         self._one_packet = (C.c_void_p * 1)()
         self._one_len = (C.c_size_t * 1)()
@@ -237,43 +250,64 @@ class H263State:
         w, h = int(hdr["width"]), int(hdr["height"])
         if w == 0 or h == 0:
             w = h = 16  # no usable size in the header: the parse inside decode_step reports the reference's error
-        if self.ctx is None or w > self.ctx.max_width or h > self.ctx.max_height:
-            self.ctx = Context(self.device, 1, max(w, 16), max(h, 16))
-            self._has_picture = False
+        # A picture larger than the context needs a bigger one.  It replaces the old context only once the packet has
+        # decoded (a size change can only succeed on an I picture, which needs no reference planes): a packet that
+        # fails leaves parser, context and last picture as they were (state.rs:120-137).
+        ctx = self.ctx
+        if ctx is None or w > ctx.max_width or h > ctx.max_height:
+            ctx = Context(self.device, 1, max(w, 16), max(h, 16))
         L = _lib.lib()
         size = w * h * 4
-        if size != self._rgba_size:
-            if self._rgba_host:
+        if size > self._ring_size:
+            # both pinned buffers grow together; nothing may still be copying into the old ones
+            if self.ctx is not None:
                 self.ctx.sync()
-                L.h263cu_free_pinned(self._rgba_host)
-            self._rgba_host = L.h263cu_alloc_pinned(size)
-            if not self._rgba_host:
-                self._rgba_size = 0
-                raise MemoryError
-            self._rgba_size = size
-            self._rgba_view = np.ctypeslib.as_array(C.cast(self._rgba_host, C.POINTER(C.c_uint8)), shape=(size,))
+            for k in range(2):
+                if self._ring[k]:
+                    L.h263cu_free_pinned(self._ring[k])
+                self._ring[k] = L.h263cu_alloc_pinned(size)
+                if not self._ring[k]:
+                    self._ring_size = 0
+                    raise MemoryError
+            self._ring_size = size
+        pos = self._ring_pos ^ 1  # the buffer that does not hold the last picture
         nd = C.c_uint32(0)
         self._one_packet[0], self._one_len[0], self._one_err[0] = buf.ctypes.data, buf.size, 0
-        _lib.check(L.h263cu_decode_step(self.ctx.h, self._one_parser, self._one_packet, self._one_len, self._one_id.ctypes.data, 1, 1,
-                                        self.out_flags, self._rgba_host, 0, self._one_err.ctypes.data, C.byref(nd)))
+        _lib.check(L.h263cu_decode_step(ctx.h, self._one_parser, self._one_packet, self._one_len, self._one_id.ctypes.data, 1, 1,
+                                        self.out_flags, self._ring[pos], 0, self._one_err.ctypes.data, C.byref(nd)))
         if self._one_err[0]:
             raise _lib.H263Error(int(self._one_err[0]))
-        self.ctx.sync()
+        if ctx is not self.ctx and self.ctx is not None:
+            self.ctx.sync()  # the old context may still be copying the previous picture back
+        self.ctx = ctx
+        self._ring_pos = pos
+        self._rgba_view = np.ctypeslib.as_array(C.cast(self._ring[pos], C.POINTER(C.c_uint8)), shape=(size,))
         self._has_picture = True
+        self._pending = True
+        if not self.pipelined:
+            self._wait()
+
+    def _wait(self):
+        """Wait for the picture queued last: its planes are reconstructed and its RGBA has arrived in host memory."""
+        if self._pending:
+            self.ctx.readback_wait(0)
+            self._pending = False
 
     def __del__(self):
-        if getattr(self, "_rgba_host", None):
-            try:
-                if self.ctx is not None:
-                    self.ctx.sync()
-                _lib.lib().h263cu_free_pinned(self._rgba_host)
-            except Exception:
-                pass
-            self._rgba_host = None
+        try:
+            if getattr(self, "ctx", None) is not None:
+                self.ctx.sync()
+            for k in range(2):
+                if self._ring[k]:
+                    _lib.lib().h263cu_free_pinned(self._ring[k])
+                    self._ring[k] = None
+        except Exception:
+            pass
 
     def get_last_picture(self):
         if not self._has_picture:
             return None
+        self._wait()
         i = self.ctx.stream_info(0)
         y, cb, cr = self.ctx.read_yuv(0)
         return DecodedPicture(i["width"], i["height"], i["pic_type"], i["pquant"], i["tr"], y, cb, cr)
@@ -292,11 +326,13 @@ class H263State:
         never holds more than those two plane slots per stream, so there is nothing to free."""
         return None
 
-    def get_last_rgba(self):
-        """RGBA of the last picture (fused yuv420_to_rgba, or deblock + yuv420_to_rgba)."""
+    def get_last_rgba(self, copy=True):
+        """RGBA of the last picture (fused yuv420_to_rgba, or deblock + yuv420_to_rgba).  copy=False returns a view of
+        the pinned read-back buffer, valid until the picture after next is queued (two buffers alternate)."""
         if not self._has_picture:
             return None
-        return self._rgba_view.copy()  # read back by decode_next_picture; the pinned buffer is reused by the next call
+        self._wait()
+        return self._rgba_view.copy() if copy else self._rgba_view
 
 
 class BatchDecoder:
@@ -342,3 +378,67 @@ class BatchDecoder:
             self.ctx.h, plan["parsers"], plan["packets"], plan["lens"], plan["ids"].ctypes.data, plan["n"], self.threads,
             out_flags, host_rgba, rgba_stride, plan["errs"].ctypes.data, C.byref(nd)))
         return plan["errs"]
+
+
+class DeviceGroup:
+    """Several GPUs driven from ONE process: one context per device, one shared pool of parser threads
+    (h263cu_group_*, SURVEY.md 8e).  Global stream s lives on device s % n_devices, slot s // n_devices; with a host
+    buffer the RGBA of stream s lands at index (s % n_devices) * streams_per_device + s // n_devices."""
+
+    def __init__(self, devices, streams_per_device, max_width, max_height, decoder_options=SORENSON_SPARK_BITSTREAM, threads=0):
+        self.L = _lib.lib()
+        self.devices = list(devices)
+        self.streams_per_device = streams_per_device
+        dv = (C.c_int * len(self.devices))(*self.devices)
+        err = C.c_int(0)
+        self.h = self.L.h263cu_group_create(dv, len(self.devices), streams_per_device, max_width, max_height, threads, C.byref(err))
+        if not self.h:
+            raise H263Error(err.value)
+        self.n = streams_per_device * len(self.devices)
+        self.parsers = [frontend.Parser(decoder_options) for _ in range(self.n)]
+        self.ctxs = [Context(d, streams_per_device, max_width, max_height, _borrowed=self.L.h263cu_group_ctx(self.h, k))
+                     for k, d in enumerate(self.devices)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            for c in self.ctxs:
+                c.close()
+            self.L.h263cu_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def position(self, stream):
+        """Index of a global stream's picture in the host RGBA buffer (device-major)."""
+        nd = len(self.devices)
+        return (stream % nd) * self.streams_per_device + stream // nd
+
+    def where(self, stream):
+        """(context, local slot) of a global stream."""
+        nd = len(self.devices)
+        return self.ctxs[stream % nd], stream // nd
+
+    def plan_step(self, packets, stream_ids=None):
+        n = len(packets)
+        ids = np.arange(n, dtype=np.uint32) if stream_ids is None else np.ascontiguousarray(stream_ids, np.uint32)
+        bufs = [np.frombuffer(pk, np.uint8) if not isinstance(pk, np.ndarray) else pk for pk in packets]
+        return {
+            "n": n, "bufs": bufs, "ids": ids,
+            "parsers": (C.c_void_p * n)(*[self.parsers[min(int(s), self.n - 1)].h for s in ids]),
+            "packets": (C.c_void_p * n)(*[b.ctypes.data for b in bufs]),
+            "lens": (C.c_size_t * n)(*[b.size for b in bufs]),
+            "errs": np.zeros(n, np.int32),
+        }
+
+    def decode_planned(self, plan, out_flags=_lib.OUT_RGBA, host_rgba=None, rgba_stride=0):
+        nd = C.c_uint32(0)
+        _lib.check(self.L.h263cu_group_decode_step(self.h, plan["parsers"], plan["packets"], plan["lens"], plan["ids"].ctypes.data,
+                                                   plan["n"], out_flags, host_rgba, rgba_stride, plan["errs"].ctypes.data, C.byref(nd)))
+        return plan["errs"]
+
+    def decode_step(self, packets, out_flags=_lib.OUT_RGBA, stream_ids=None, host_rgba=None, rgba_stride=0):
+        return self.decode_planned(self.plan_step(packets, stream_ids), out_flags, host_rgba, rgba_stride)
+
+    def sync(self):
+        check(self.L.h263cu_group_sync(self.h))

@@ -16,7 +16,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libh263cu.so")
-SOURCES = ["kernels.cu", "recon_tile.cu", "deblock_tile.cu", "context.cu", "frontend.cpp", "synth.cpp", "flv.cpp"]
+SOURCES = ["kernels.cu", "recon_tile.cu", "deblock_tile.cu", "context.cu", "frontend.cpp", "flv.cpp"]
+# the synthetic stream generator is its own library (g++ only): test / benchmark tooling, not part of the decode path
+SYNTH_OUT = os.path.join(HERE, "libh263synth.so")
+SYNTH_DEPS = ["synth.cpp", "bitio.hpp", "vlc_codes.inc", os.path.join("..", "..", "include", "h263synth.h")]
 DEPS = SOURCES + ["kernels.cuh", "recon_common.cuh", "device_math.cuh", "bitio.hpp", "vlc_codes.inc", os.path.join("..", "..", "include", "h263cu.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
@@ -36,7 +39,20 @@ def up_to_date():
     return all(os.path.getmtime(os.path.join(CSRC, d)) <= t for d in DEPS)
 
 
+def build_synth(force=False):
+    if not force and os.path.exists(SYNTH_OUT) and all(
+            os.path.getmtime(os.path.join(CSRC, d)) <= os.path.getmtime(SYNTH_OUT) for d in SYNTH_DEPS):
+        return SYNTH_OUT
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SYNTH_OUT, os.path.join(CSRC, "synth.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed: " + " ".join(cmd))
+    return SYNTH_OUT
+
+
 def build(force=False, verbose=False):
+    build_synth(force)
     if not force and up_to_date():
         return OUT
     cmd = nvcc_cmd(["-Xptxas", "-v"] if verbose else [])

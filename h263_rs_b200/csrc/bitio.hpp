@@ -10,6 +10,8 @@
 
 namespace h263fe {
 
+#define H263_AI __attribute__((always_inline)) inline
+
 struct VlcCode {
     const char* bits;
     int len;
@@ -40,46 +42,40 @@ const VlcCode* vlc_codes(int id, int* count);
 
 // Reads MSB-first from an in-memory packet.  A read of n bits fails (returns false)
 // iff fewer than n bits remain -- the reference's UnexpectedEof (reader.rs:49-75).
-// The next bits sit MSB-aligned in a 64-bit window that is refilled from memory only when fewer than 32
-// of them are left, so the dependent chain per symbol is shift -> table load -> shift instead of a fresh
-// 8-byte load + byte swap per read.
 struct BitReader {
     const uint8_t* data;
     size_t total_bits;
 
     BitReader(const uint8_t* d, size_t len) : data(d), total_bits(len * 8), pos_(0) { refill(); }
-    size_t pos() const { return pos_; }
-    size_t avail() const { return total_bits - pos_; }
-    void seek(size_t p) {
+    H263_AI size_t pos() const { return pos_; }
+    H263_AI size_t avail() const { return total_bits - pos_; }
+    H263_AI void seek(size_t p) {
         pos_ = p;
         refill();
     }
 
     // Next n (<= 32) bits, zero padded past the end of the packet.
-    inline uint32_t peek_padded(unsigned n) const { return n == 0 ? 0u : (uint32_t)(win_ >> (64 - n)); }
-    inline void consume(unsigned n) {
+    H263_AI uint32_t peek_padded(unsigned n) const { return n == 0 ? 0u : (uint32_t)(win_ >> (64 - n)); }
+    // The window is rebuilt from memory after every consume: one unaligned 8-byte load + byte swap + shift, no
+    // data-dependent branch (the only branch is the end-of-packet test, taken in the last 8 bytes).  At least 57
+    // bits are valid after every call, so any field or code + sign (<= 32 bits) can be taken from it.
+    H263_AI void consume(unsigned n) {
         pos_ += n;
-        if (n >= have_) {
-            refill();
-        } else {
-            win_ <<= n;
-            have_ -= n;
-            if (have_ < 32) refill();
-        }
+        refill();
     }
-    inline bool read(unsigned n, uint32_t* out) {
+    H263_AI bool read(unsigned n, uint32_t* out) {
         if (n > avail()) return false;
         *out = peek_padded(n);
         consume(n);
         return true;
     }
-    inline bool read_signed(unsigned n, int32_t* out) {
+    H263_AI bool read_signed(unsigned n, int32_t* out) {
         uint32_t v;
         if (!read(n, &v)) return false;
         *out = (int32_t)(v << (32 - n)) >> (32 - n);
         return true;
     }
-    inline bool skip(unsigned n) {
+    H263_AI bool skip(unsigned n) {
         if (n > avail()) return false;
         consume(n);
         return true;
@@ -87,8 +83,17 @@ struct BitReader {
     // One VLC symbol.  Returns false on EOF (the serial walk would run out of bits before
     // reaching a leaf: codes are prefix free, so that happens iff the zero-padded lookup
     // lands on a code longer than what is left).
-    inline bool read_vlc(const VlcTable& t, const VlcEntry** out) {
+    H263_AI bool read_vlc(const VlcTable& t, const VlcEntry** out) {
         const VlcEntry& e = t.lut[peek_padded((unsigned)t.max_len)];
+        if (e.len() > avail()) return false;
+        consume(e.len());
+        *out = &e;
+        return true;
+    }
+    // The same with the table held by the caller as a raw pointer + width (locals of the caller: no reload of the
+    // vector's fields after every store the compiler cannot disambiguate)
+    H263_AI bool read_vlc(const VlcEntry* __restrict lut, unsigned max_len, const VlcEntry** out) {
+        const VlcEntry& e = lut[(uint32_t)(win_ >> (64 - max_len))];
         if (e.len() > avail()) return false;
         consume(e.len());
         *out = &e;
@@ -96,7 +101,7 @@ struct BitReader {
     }
     // One VLC symbol followed by `extra` (<= 8) plain bits, fetched from the same window (max_len + extra <= 32).
     // EOF semantics as two separate reads: the code must fit, then the extra bits must fit.
-    inline bool read_vlc_bits(const VlcTable& t, unsigned extra, const VlcEntry** out, uint32_t* bits, bool* eof_in_extra) {
+    H263_AI bool read_vlc_bits(const VlcTable& t, unsigned extra, const VlcEntry** out, uint32_t* bits, bool* eof_in_extra) {
         const uint64_t w = win_;
         const VlcEntry& e = t.lut[(uint32_t)(w >> (64 - t.max_len))];
         const unsigned len = e.len();
@@ -117,24 +122,25 @@ struct BitReader {
         consume(len + extra);
         return true;
     }
+    // the window itself, for decoders that look at more than one field per fetch (frontend.cpp's TCOEF loop)
+    H263_AI uint64_t window() const { return win_; }
 
   private:
     size_t pos_;
-    uint64_t win_;   // bits pos_.. MSB-aligned, zero padded past the end of the packet
-    unsigned have_;  // how many leading bits of win_ are backed by the packet or its zero padding (>= 32 after a refill)
+    uint64_t win_;  // bits pos_.. MSB-aligned (at least 57 of them), zero padded past the end of the packet
 
-    inline void refill() {
+    H263_AI void refill() {
         const size_t byte = pos_ >> 3, nbytes = total_bits >> 3;
-        uint64_t w = 0;
-        if (byte + 8 <= nbytes) {
+        uint64_t w;
+        if (__builtin_expect(byte + 8 <= nbytes, 1)) {
             uint64_t raw;
             std::memcpy(&raw, data + byte, 8);
             w = __builtin_bswap64(raw);
         } else {
+            w = 0;
             for (size_t i = 0; i < 8; i++) w = (w << 8) | (byte + i < nbytes ? data[byte + i] : 0);
         }
         win_ = w << (pos_ & 7);
-        have_ = 64 - (unsigned)(pos_ & 7);  // >= 57
     }
 };
 

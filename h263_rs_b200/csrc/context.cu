@@ -19,6 +19,15 @@
 
 using namespace h263dev;
 
+// frontend.cpp: the threaded parse with the parsers' state change held back until parse_step_finish(accept)
+namespace h263fe {
+int parse_step_deferred(h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                        const uint32_t* stream_ids, uint32_t n, int threads, h263cu_pic* pics, h263cu_mb* mbs, uint32_t mb_cap,
+                        h263cu_event* events, uint32_t ev_cap, uint32_t* n_pics_out, uint32_t* n_mbs_out, uint32_t* n_units_out,
+                        int* per_pic_err, int32_t* pic_of_input, uint32_t max_w, uint32_t max_h);
+void parse_step_finish(h263cu_parser* const* parsers, uint32_t n, bool accept);
+}  // namespace h263fe
+
 extern "C" const uint8_t h263cu_quant_to_strength[32] = H263_QUANT_TO_STRENGTH;
 
 namespace {
@@ -163,7 +172,7 @@ int step_reserve(h263cu_step* s, size_t n_mbs, size_t n_units) {
     return 0;
 }
 
-int prof_begin(h263cu_ctx* c, cudaEvent_t* a, cudaEvent_t* b) {
+int prof_take(h263cu_ctx* c, cudaEvent_t* a, cudaEvent_t* b) {
     for (cudaEvent_t* e : {a, b}) {
         if (!c->prof_free.empty()) {
             *e = c->prof_free.back();
@@ -172,7 +181,6 @@ int prof_begin(h263cu_ctx* c, cudaEvent_t* a, cudaEvent_t* b) {
             CU_TRY(cudaEventCreate(e));
         }
     }
-    CU_TRY(cudaEventRecord(*a, c->s_main));
     return 0;
 }
 void prof_end(h263cu_ctx* c, cudaEvent_t a, cudaEvent_t b, int kind) {
@@ -183,13 +191,15 @@ void prof_end(h263cu_ctx* c, cudaEvent_t a, cudaEvent_t b, int kind) {
 // Validates a step against the context and the per-stream state, builds the PicDev array,
 // enqueues the kernels on s_main and advances the per-stream reference bookkeeping
 // (state.rs:464-483: the picture just decoded becomes the reference of the next one).
+// Nothing of the per-stream state changes unless the kernels have been enqueued: a step that is
+// refused, or that fails on the way to the launch, leaves every stream as it was.
 int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     const uint32_t n = (uint32_t)s->pics.size();
     if (n == 0) return 0;
-    if (n > 65535) return H263CU_ERR_CAPACITY;
+    if (n > 65535) return H263CU_ERR_CAPACITY;  // h263cu_mb.pic is 16 bits wide
     const bool want_rgba = (out_flags & H263CU_OUT_RGBA) != 0;
     const bool want_deblock = want_rgba && (out_flags & H263CU_OUT_DEBLOCK) != 0;
-    c->stamp++;
+    const uint32_t stamp = ++c->stamp;  // marks the streams named by this step (duplicate check only)
     uint32_t max_w = 0, max_h = 0;
     bool tiled = true, aligned16 = true, wide_mv = false;
     for (uint32_t i = 0; i < n; i++) {
@@ -203,8 +213,8 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
             p.n_mbs != (uint32_t)p.mb_w * p.mb_h)
             return H263CU_ERR_BAD_ARGUMENT;
         StreamState& st = c->streams[p.stream];
-        if (st.stamp == c->stamp) return H263CU_ERR_BAD_ARGUMENT;  // a stream appears once per step
-        st.stamp = c->stamp;
+        if (st.stamp == stamp) return H263CU_ERR_BAD_ARGUMENT;  // a stream appears once per step
+        st.stamp = stamp;
         if (p.flags & H263CU_PICFLAG_HAS_INTER) {
             if (!st.has_pic) return H263CU_ERR_UNCODED_IFRAME_BLOCKS;             // gather.rs:149
             if (st.w != p.width || st.h != p.height) return H263CU_ERR_REFERENCE_WOULD_ABORT;
@@ -221,13 +231,12 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     int e = ensure_pic_ring(c, n);
     if (e) return e;
     const int slot = c->pic_ring_pos;
-    c->pic_ring_pos = (c->pic_ring_pos + 1) % h263cu_ctx::PIC_RING;
     CU_TRY(cudaEventSynchronize(c->pics_done[slot]));
     const int rgba_ring = (int)(c->rgba_parity & 1u);
     PicDev* hp = c->h_pics[slot];
     for (uint32_t i = 0; i < n; i++) {
         const h263cu_pic& p = s->pics[i];
-        StreamState& st = c->streams[p.stream];
+        const StreamState& st = c->streams[p.stream];
         const int ref_slot = st.cur_slot, new_slot = st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot;
         PicDev d;
         std::memset(&d, 0, sizeof(d));
@@ -249,13 +258,15 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         d.strength = h263cu_quant_to_strength[p.pquant & 31];
         d.flags = p.flags;
         hp[i] = d;
-        // bookkeeping
-        st.cur_slot = (uint8_t)new_slot;
-        st.has_pic = true;
-        st.w = p.width, st.h = p.height;
-        st.pic_type = p.pic_type, st.pquant = p.pquant, st.tr = p.temporal_reference;
-        st.rgba_slot = want_rgba ? (int8_t)rgba_ring : (int8_t)-1;
-        st.padded = tiled;
+    }
+    cudaEvent_t pa = nullptr, pb = nullptr, qa = nullptr, qb = nullptr;
+    if (c->profiling) {
+        // the event pairs are taken before anything is enqueued: a failure here leaves no trace
+        if ((e = prof_take(c, &pa, &pb))) return e;
+        if (want_deblock && (e = prof_take(c, &qa, &qb))) {
+            c->prof_free.push_back(pa), c->prof_free.push_back(pb);
+            return e;
+        }
     }
     // the descriptors travel on their own stream, so the copy overlaps the previous step's kernels
     // (pics_done[slot] was waited for above: the kernels that read this ring slot four steps ago are done)
@@ -266,24 +277,34 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         // do not overwrite an RGBA ring slot that is still being read back
         CU_TRY(cudaStreamWaitEvent(c->s_main, c->rgba_read[rgba_ring], 0));
     }
-    cudaEvent_t pa = nullptr, pb = nullptr;
-    if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
+    if (pa) cudaEventRecord(pa, c->s_main);
     const Pools pools{c->y_pool, c->c_pool, c->rgba_pool, c->pitch_y, c->pitch_c, c->rgba_pitch};
     launch_recon(c->d_pics[slot], s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, tiled ? (aligned16 ? 1 : 2) : 0, wide_mv, pools,
                  &c->rgba_map, c->s_main);
-    c->launches++;
-    if (tiled) c->tiled_launches++;
-    if (c->profiling) prof_end(c, pa, pb, 0);
+    if (pa) prof_end(c, pa, pb, 0);
     if (want_deblock) {
-        if (c->profiling && (e = prof_begin(c, &pa, &pb))) return e;
+        if (qa) cudaEventRecord(qa, c->s_main);
         if (aligned16 && c->force_kernel != 1)
             launch_deblock_rgba_tile(c->d_pics[slot], n, max_w, max_h, c->s_main);
         else
             launch_deblock_rgba(c->d_pics[slot], n, max_w, max_h, c->s_main);
-        c->launches++;
-        if (c->profiling) prof_end(c, pa, pb, 1);
+        if (qa) prof_end(c, qa, qb, 1);
     }
     CU_TRY(cudaGetLastError());
+    // ---- the step is on the device: commit the bookkeeping ----
+    c->pic_ring_pos = (c->pic_ring_pos + 1) % h263cu_ctx::PIC_RING;
+    c->launches += want_deblock ? 2 : 1;
+    if (tiled) c->tiled_launches++;
+    for (uint32_t i = 0; i < n; i++) {
+        const h263cu_pic& p = s->pics[i];
+        StreamState& st = c->streams[p.stream];
+        st.cur_slot = (uint8_t)(st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot);
+        st.has_pic = true;
+        st.w = p.width, st.h = p.height;
+        st.pic_type = p.pic_type, st.pquant = p.pquant, st.tr = p.temporal_reference;
+        st.rgba_slot = want_rgba ? (int8_t)rgba_ring : (int8_t)-1;
+        st.padded = tiled;
+    }
     CU_TRY(cudaEventRecord(c->pics_done[slot], c->s_main));
     if (want_rgba) {
         CU_TRY(cudaEventRecord(c->rgba_written[rgba_ring], c->s_main));
@@ -292,12 +313,51 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     return 0;
 }
 
+// Checks caller-built side info before it goes to the device, where the kernels index with it unchecked: every
+// record belongs to the picture whose range it lies in and sits at its raster position, its events stay inside the
+// picture's share of the event array.  HAS_INTER / MV_IN_RANGE are derived from the records, not taken on trust: a
+// picture with an inter macroblock gets HAS_INTER, one with a vector beyond [-32, 31] loses MV_IN_RANGE (and takes
+// the clamped-fetch instantiation).  Side info produced by the library's own parser skips this pass.
+int validate_side_info(std::vector<h263cu_pic>& pics, const h263cu_mb* mbs, uint32_t n_mbs, uint32_t n_units) {
+    for (size_t i = 0; i < pics.size(); i++) {
+        h263cu_pic& p = pics[i];
+        if ((uint64_t)p.first_mb + p.n_mbs > n_mbs || (uint64_t)p.first_event + p.n_event_units > n_units ||
+            p.n_mbs != (uint32_t)p.mb_w * p.mb_h || p.mb_w == 0)
+            return H263CU_ERR_BAD_ARGUMENT;
+        bool any_inter = false, in_range = true;
+        const h263cu_mb* m = mbs + p.first_mb;
+        for (uint32_t k = 0; k < p.n_mbs; k++, m++) {
+            if (m->pic != i || (uint32_t)m->mby * p.mb_w + m->mbx != k || m->mbx >= p.mb_w) return H263CU_ERR_BAD_ARGUMENT;
+            uint32_t ev = 0;
+            for (int b = 0; b < 6; b++) ev += m->nev[b];
+            if (m->flags & H263CU_MB_WIDE) ev *= 2;
+            if ((uint64_t)m->ev_off + ev > p.n_event_units) return H263CU_ERR_BAD_ARGUMENT;
+            if (m->flags & H263CU_MB_INTER) {
+                any_inter = true;
+                for (int b = 0; b < 4; b++)
+                    in_range &= m->u.mv[b][0] >= -32 && m->u.mv[b][0] <= 31 && m->u.mv[b][1] >= -32 && m->u.mv[b][1] <= 31;
+            }
+        }
+        if (any_inter) p.flags |= H263CU_PICFLAG_HAS_INTER;
+        if (!in_range) p.flags &= (uint8_t)~H263CU_PICFLAG_MV_IN_RANGE;
+    }
+    return 0;
+}
+
 int upload_into(h263cu_ctx* c, h263cu_step* s, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
-                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, cudaStream_t stream) {
+                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, cudaStream_t stream, bool trusted) {
     int e = step_reserve(s, n_mbs, n_units);
     if (e) return e;
-    s->pics.assign(pics, pics + n_pics);
+    try {
+        s->pics.assign(pics, pics + n_pics);
+    } catch (const std::bad_alloc&) {
+        return H263CU_ERR_OUT_OF_MEMORY;
+    }
     s->n_mbs = n_mbs, s->n_units = n_units;
+    if (!trusted && (e = validate_side_info(s->pics, mbs, n_mbs, n_units))) {
+        s->pics.clear();
+        return e;
+    }
     if (n_mbs) CU_TRY(cudaMemcpyAsync(s->d_mbs, mbs, (size_t)n_mbs * sizeof(h263cu_mb), cudaMemcpyHostToDevice, stream));
     if (n_units)
         CU_TRY(cudaMemcpyAsync(s->d_events, events, (size_t)n_units * sizeof(h263cu_event), cudaMemcpyHostToDevice, stream));
@@ -330,8 +390,7 @@ int make_rgba_map(CUtensorMap* map, void* base, uint64_t pitch, uint64_t rows) {
     }
     const cuuint64_t dims[2] = {pitch, rows}, strides[1] = {pitch};
     const cuuint32_t box[2] = {64, 16}, es[2] = {1, 1};
-    const CUtensorMapSwizzle sw = recon_tile_uses_tma() == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B;
-    if (enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+    if (enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return H263CU_ERR_CUDA;
     return 0;
@@ -415,7 +474,7 @@ h263cu_ctx* h263cu_create(int device, uint32_t max_streams, uint32_t max_width, 
     if (cudaMalloc((void**)&c->rgba_pool, c->rgba_slot * 2 * max_streams + pad) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
     {
         // TMA tensor map over the RGBA pool: the reconstruction kernel stores one 64-byte x 16-row box per macroblock
-        // (cp.async.bulk.tensor.2d) from a 128B-swizzled shared-memory tile
+        // (cp.async.bulk.tensor.2d) from a shared-memory tile
         const int e = make_rgba_map(&c->rgba_map, c->rgba_pool, c->rgba_pitch, (uint64_t)2 * max_streams * c->mbh * 16);
         if (e) return fail(e);
     }
@@ -516,7 +575,7 @@ h263cu_step* h263cu_step_upload(h263cu_ctx* c, const h263cu_pic* pics, uint32_t 
         *err = H263CU_ERR_OUT_OF_MEMORY;
         return nullptr;
     }
-    int e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_main);
+    int e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_main, false);
     if (e) {
         free_step_buffers(s);
         delete s;
@@ -543,21 +602,21 @@ int h263cu_step_run(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
 }
 
 static int submit_common(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs, uint32_t n_mbs,
-                         const h263cu_event* events, uint32_t n_units, uint32_t out_flags) {
+                         const h263cu_event* events, uint32_t n_units, uint32_t out_flags, bool trusted = false) {
     if (!c || !pics || (!mbs && n_mbs) || (!events && n_units)) return H263CU_ERR_BAD_ARGUMENT;
     cudaSetDevice(c->device);
     const int slot = c->ring_pos;
-    c->ring_pos ^= 1;
     h263cu_step* s = &c->ring[slot];
     // the copy engine may not overwrite side info that a kernel is still reading
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, c->ring_run_done[slot], 0));
     if (n_mbs > s->mb_cap || (size_t)n_units + 8 > s->ev_cap) CU_TRY(cudaEventSynchronize(c->ring_run_done[slot]));
-    int e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_h2d);
+    int e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_h2d, trusted);
     if (e) return e;
     CU_TRY(cudaEventRecord(c->ring_h2d_done[slot], c->s_h2d));
     CU_TRY(cudaStreamWaitEvent(c->s_main, c->ring_h2d_done[slot], 0));
     e = run_step(c, s, out_flags);
     if (e) return e;
+    c->ring_pos ^= 1;  // the ring slot is taken only by a step that runs
     CU_TRY(cudaEventRecord(c->ring_run_done[slot], c->s_main));
     return 0;
 }
@@ -567,12 +626,12 @@ int h263cu_submit_step(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, c
     return submit_common(c, pics, n_pics, mbs, n_mbs, events, n_units, out_flags);
 }
 
-int h263cu_submit_step_readback(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
-                                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, uint32_t out_flags,
-                                uint8_t* host_rgba, const uint64_t* rgba_offsets) {
+static int submit_readback(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs, uint32_t n_mbs,
+                           const h263cu_event* events, uint32_t n_units, uint32_t out_flags, uint8_t* host_rgba,
+                           const uint64_t* rgba_offsets, bool trusted) {
     if (!host_rgba) return H263CU_ERR_BAD_ARGUMENT;
     out_flags |= H263CU_OUT_RGBA;
-    int e = submit_common(c, pics, n_pics, mbs, n_mbs, events, n_units, out_flags);
+    int e = submit_common(c, pics, n_pics, mbs, n_mbs, events, n_units, out_flags, trusted);
     if (e) return e;
     const int ring = (int)((c->rgba_parity - 1) & 1u);  // the slot run_step just wrote
     CU_TRY(cudaStreamWaitEvent(c->s_d2h, c->rgba_written[ring], 0));
@@ -605,9 +664,17 @@ int h263cu_submit_step_readback(h263cu_ctx* c, const h263cu_pic* pics, uint32_t 
     return 0;
 }
 
-int h263cu_decode_step(h263cu_ctx* c, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
-                       const uint32_t* stream_ids, uint32_t n, int threads, uint32_t out_flags, uint8_t* host_rgba,
-                       uint64_t rgba_stride, int* per_pic_err, uint32_t* n_decoded) {
+int h263cu_submit_step_readback(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
+                                uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, uint32_t out_flags,
+                                uint8_t* host_rgba, const uint64_t* rgba_offsets) {
+    return submit_readback(c, pics, n_pics, mbs, n_mbs, events, n_units, out_flags, host_rgba, rgba_offsets, false);
+}
+
+// The body of h263cu_decode_step; `positions` (may be NULL: input i sits at position i) says where input i's RGBA goes in
+// host_rgba, in units of rgba_stride (the group form scatters the pictures of one device over a buffer shared by all).
+static int decode_step_scattered(h263cu_ctx* c, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                                 const uint32_t* stream_ids, uint32_t n, int threads, uint32_t out_flags, uint8_t* host_rgba,
+                                 uint64_t rgba_stride, const uint32_t* positions, int* per_pic_err, uint32_t* n_decoded) {
     if (!c || !parsers || !packets || !lens) return H263CU_ERR_BAD_ARGUMENT;
     if (n_decoded) *n_decoded = 0;
     if (n == 0) return 0;
@@ -618,19 +685,15 @@ int h263cu_decode_step(h263cu_ctx* c, h263cu_parser* const* parsers, const uint8
     for (uint32_t i = 0; i < n; i++) bytes += lens[i];
     const size_t mb_need = (size_t)n * c->mbw * c->mbh, ev_need = bytes * 16 / 3 + 16 * (size_t)n;
     if (mb_need > 0xFFFFFFFFull || ev_need > 0xFFFFFFFFull) return H263CU_ERR_CAPACITY;
-    // Everything the device stage could refuse is checked before any parser advances, so that a failing call leaves
-    // every stream as it was (decode_next_picture is a transaction, state.rs:120-137): stream ids in range and named
-    // once, pictures no larger than the context.
+    // Stream ids are checked before anything is parsed; a picture larger than the context fails as that picture's
+    // error inside the parse.  The parsers advance only when the device stage has accepted the step, so a failing
+    // call leaves every stream as it was (decode_next_picture is a transaction, state.rs:120-137).
     c->decode_epoch++;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t sid = stream_ids ? stream_ids[i] : i;
         if (sid >= c->max_streams) return H263CU_ERR_CAPACITY;
         if (c->streams[sid].seen == c->decode_epoch) return H263CU_ERR_BAD_ARGUMENT;
         c->streams[sid].seen = c->decode_epoch;
-        h263cu_pic hdr;
-        if (packets[i] && parsers[i] && h263cu_peek_picture(h263cu_parser_options(parsers[i]), packets[i], lens[i], &hdr) == 0 &&
-            (hdr.width > c->max_w || hdr.height > c->max_h))
-            return H263CU_ERR_CAPACITY;
     }
     const int slot = c->ring_pos;  // the ring slot submit_common is about to use
     h263cu_ctx::Staging& st = c->staging[slot];
@@ -640,18 +703,43 @@ int h263cu_decode_step(h263cu_ctx* c, h263cu_parser* const* parsers, const uint8
     if ((e = grow_pinned(&st.pics, &st.pic_cap, n)) || (e = grow_pinned(&st.mbs, &st.mb_cap, mb_need)) ||
         (e = grow_pinned(&st.events, &st.ev_cap, ev_need)))
         return e;
-    c->pic_of_input.resize(n);
+    try {
+        c->pic_of_input.resize(n);
+    } catch (const std::bad_alloc&) {
+        return H263CU_ERR_OUT_OF_MEMORY;
+    }
     uint32_t np = 0, nm = 0, nu = 0;
-    e = h263cu_parse_step(parsers, packets, lens, stream_ids, n, threads, st.pics, st.mbs, (uint32_t)st.mb_cap, st.events,
-                          (uint32_t)st.ev_cap, &np, &nm, &nu, per_pic_err, c->pic_of_input.data());
-    if (e) return e;
+    e = h263fe::parse_step_deferred(parsers, packets, lens, stream_ids, n, threads, st.pics, st.mbs, (uint32_t)st.mb_cap, st.events,
+                                    (uint32_t)st.ev_cap, &np, &nm, &nu, per_pic_err, c->pic_of_input.data(), c->max_w, c->max_h);
+    if (e) {
+        h263fe::parse_step_finish(parsers, n, false);
+        return e;
+    }
     if (n_decoded) *n_decoded = np;
     if (np == 0) return 0;
-    if (!host_rgba) return submit_common(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags);
-    c->rgba_offsets.resize(np);
-    for (uint32_t i = 0; i < n; i++)
-        if (c->pic_of_input[i] >= 0) c->rgba_offsets[(size_t)c->pic_of_input[i]] = (uint64_t)i * rgba_stride;
-    return h263cu_submit_step_readback(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags, host_rgba, c->rgba_offsets.data());
+    if (!host_rgba) {
+        e = submit_common(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags, true);
+    } else {
+        try {
+            c->rgba_offsets.resize(np);
+        } catch (const std::bad_alloc&) {
+            h263fe::parse_step_finish(parsers, n, false);
+            return H263CU_ERR_OUT_OF_MEMORY;
+        }
+        for (uint32_t i = 0; i < n; i++)
+            if (c->pic_of_input[i] >= 0) c->rgba_offsets[(size_t)c->pic_of_input[i]] = (uint64_t)(positions ? positions[i] : i) * rgba_stride;
+        e = submit_readback(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags, host_rgba, c->rgba_offsets.data(), true);
+    }
+    // the device stage has the step (or refused it): only now do the parsers move on
+    h263fe::parse_step_finish(parsers, n, e == 0);
+    return e;
+}
+
+int h263cu_decode_step(h263cu_ctx* c, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                       const uint32_t* stream_ids, uint32_t n, int threads, uint32_t out_flags, uint8_t* host_rgba,
+                       uint64_t rgba_stride, int* per_pic_err, uint32_t* n_decoded) {
+    return decode_step_scattered(c, parsers, packets, lens, stream_ids, n, threads, out_flags, host_rgba, rgba_stride, nullptr,
+                                 per_pic_err, n_decoded);
 }
 
 int h263cu_sync(h263cu_ctx* c) {
@@ -789,20 +877,168 @@ int h263cu_profile_read(h263cu_ctx* c, double* ms2, uint64_t* launches2) {
     return 0;
 }
 
-// ---- stateless drop-ins: host buffers in, host buffers out ---------------------------------
-static std::mutex g_scratch_mutex;
-static uint8_t* g_scratch = nullptr;
-static size_t g_scratch_cap = 0;
-
-static int scratch_reserve(size_t bytes) {
-    if (bytes <= g_scratch_cap) return 0;
-    if (g_scratch) cudaFree(g_scratch);
-    g_scratch = nullptr;
-    g_scratch_cap = 0;
-    CU_TRY(cudaMalloc((void**)&g_scratch, bytes));
-    g_scratch_cap = bytes;
+int h263cu_readback_wait(h263cu_ctx* c, uint32_t age) {
+    if (!c || age > 1) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    if (c->rgba_parity <= age) return H263CU_ERR_NO_PICTURE;  // no such step yet
+    const int ring = (int)((c->rgba_parity - 1u - age) & 1u);
+    CU_TRY(cudaEventSynchronize(c->rgba_read[ring]));
     return 0;
 }
+
+// ---- one process, several GPUs: a group of contexts fed by ONE shared pool of parser threads ----
+struct h263cu_group {
+    std::vector<h263cu_ctx*> ctx;
+    uint32_t streams_per_device = 0;
+    int threads = 0;
+    // per-device argument slices of the current step (reused)
+    struct Slice {
+        std::vector<h263cu_parser*> parsers;
+        std::vector<const uint8_t*> packets;
+        std::vector<size_t> lens;
+        std::vector<uint32_t> ids, input, pos;
+        std::vector<int> errs;
+    };
+    std::vector<Slice> slice;
+};
+
+h263cu_group* h263cu_group_create(const int* devices, uint32_t n_devices, uint32_t streams_per_device, uint32_t max_width,
+                                  uint32_t max_height, int threads, int* err) {
+    int dummy;
+    if (!err) err = &dummy;
+    *err = 0;
+    if (!devices || n_devices == 0 || n_devices > 64 || streams_per_device == 0) {
+        *err = H263CU_ERR_BAD_ARGUMENT;
+        return nullptr;
+    }
+    h263cu_group* g = new (std::nothrow) h263cu_group();
+    if (!g) {
+        *err = H263CU_ERR_OUT_OF_MEMORY;
+        return nullptr;
+    }
+    g->streams_per_device = streams_per_device, g->threads = threads;
+    try {
+        g->slice.resize(n_devices);
+    } catch (const std::bad_alloc&) {
+        delete g;
+        *err = H263CU_ERR_OUT_OF_MEMORY;
+        return nullptr;
+    }
+    for (uint32_t d = 0; d < n_devices; d++) {
+        h263cu_ctx* c = h263cu_create(devices[d], streams_per_device, max_width, max_height, 0, err);
+        if (!c) {
+            h263cu_group_destroy(g);
+            return nullptr;
+        }
+        g->ctx.push_back(c);
+    }
+    return g;
+}
+
+void h263cu_group_destroy(h263cu_group* g) {
+    if (!g) return;
+    for (h263cu_ctx* c : g->ctx) h263cu_destroy(c);
+    delete g;
+}
+
+uint32_t h263cu_group_size(const h263cu_group* g) { return g ? (uint32_t)g->ctx.size() : 0u; }
+h263cu_ctx* h263cu_group_ctx(h263cu_group* g, uint32_t index) { return g && index < g->ctx.size() ? g->ctx[index] : nullptr; }
+
+int h263cu_group_decode_step(h263cu_group* g, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                             const uint32_t* stream_ids, uint32_t n, uint32_t out_flags, uint8_t* host_rgba, uint64_t rgba_stride,
+                             int* per_pic_err, uint32_t* n_decoded) {
+    if (!g || !parsers || !packets || !lens) return H263CU_ERR_BAD_ARGUMENT;
+    if (n_decoded) *n_decoded = 0;
+    const uint32_t nd = (uint32_t)g->ctx.size();
+    try {
+        for (auto& sl : g->slice) sl.parsers.clear(), sl.packets.clear(), sl.lens.clear(), sl.ids.clear(), sl.input.clear(), sl.pos.clear();
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t sid = stream_ids ? stream_ids[i] : i;
+            const uint32_t d = sid % nd, local = sid / nd;
+            if (local >= g->streams_per_device) return H263CU_ERR_CAPACITY;
+            h263cu_group::Slice& sl = g->slice[d];
+            sl.parsers.push_back(parsers[i]), sl.packets.push_back(packets[i]), sl.lens.push_back(lens[i]);
+            sl.ids.push_back(local), sl.input.push_back(i), sl.pos.push_back(d * g->streams_per_device + local);
+        }
+        for (auto& sl : g->slice) sl.errs.assign(sl.ids.size(), 0);
+    } catch (const std::bad_alloc&) {
+        return H263CU_ERR_OUT_OF_MEMORY;
+    }
+    // Device by device: the pictures of device d are parsed on ALL of the group's parser threads and queued on d (upload,
+    // kernels and read-back are asynchronous), then the threads move on to device d + 1 while d works and copies back.
+    // No core is tied to a GPU: a device with fewer or cheaper pictures just takes less of the pool's time.
+    int first_err = 0;
+    uint32_t total = 0;
+    for (uint32_t d = 0; d < nd; d++) {
+        h263cu_group::Slice& sl = g->slice[d];
+        const uint32_t m = (uint32_t)sl.ids.size();
+        if (m == 0) continue;
+        uint32_t got = 0;
+        // RGBA of global stream s goes to host_rgba + ((s % n_devices) * streams_per_device + s / n_devices) * rgba_stride:
+        // device-major, so that the pictures of one device are contiguous and leave in few large copies
+        int e;
+        if (host_rgba) {
+            e = decode_step_scattered(g->ctx[d], sl.parsers.data(), sl.packets.data(), sl.lens.data(), sl.ids.data(), m, g->threads,
+                                      out_flags, host_rgba, rgba_stride, sl.pos.data(), sl.errs.data(), &got);
+        } else {
+            e = h263cu_decode_step(g->ctx[d], sl.parsers.data(), sl.packets.data(), sl.lens.data(), sl.ids.data(), m, g->threads, out_flags,
+                                   nullptr, 0, sl.errs.data(), &got);
+        }
+        if (e && !first_err) first_err = e;
+        total += got;
+        if (per_pic_err)
+            for (uint32_t k = 0; k < m; k++) per_pic_err[sl.input[k]] = e ? e : sl.errs[k];
+    }
+    if (n_decoded) *n_decoded = total;
+    return first_err;
+}
+
+int h263cu_group_sync(h263cu_group* g) {
+    if (!g) return H263CU_ERR_BAD_ARGUMENT;
+    int first = 0;
+    for (h263cu_ctx* c : g->ctx) {
+        const int e = h263cu_sync(c);
+        if (e && !first) first = e;
+    }
+    return first;
+}
+
+// ---- stateless drop-ins: host buffers in, host buffers out ---------------------------------
+// One scratch set per device (device buffer, pinned staging, stream), used under one lock: the calls run on the
+// device that is current on the calling thread, like any CUDA runtime call.
+namespace {
+struct DropInScratch {
+    uint8_t* dev = nullptr;
+    size_t dev_cap = 0;
+    uint8_t* pinned = nullptr;
+    size_t pinned_cap = 0;
+    cudaStream_t stream = nullptr;
+};
+std::mutex g_scratch_mutex;
+DropInScratch g_scratch[64];
+
+int scratch_get(size_t dev_bytes, size_t pinned_bytes, DropInScratch** out) {
+    int device = 0;
+    CU_TRY(cudaGetDevice(&device));
+    if (device < 0 || device >= 64) return H263CU_ERR_NO_DEVICE;
+    DropInScratch& sc = g_scratch[device];
+    if (!sc.stream) CU_TRY(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
+    if (dev_bytes > sc.dev_cap) {
+        if (sc.dev) cudaFree(sc.dev);
+        sc.dev = nullptr, sc.dev_cap = 0;
+        CU_TRY(cudaMalloc((void**)&sc.dev, dev_bytes + dev_bytes / 4));
+        sc.dev_cap = dev_bytes + dev_bytes / 4;
+    }
+    if (pinned_bytes > sc.pinned_cap) {
+        if (sc.pinned) cudaFreeHost(sc.pinned);
+        sc.pinned = nullptr, sc.pinned_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&sc.pinned, pinned_bytes + pinned_bytes / 4, cudaHostAllocDefault));
+        sc.pinned_cap = pinned_bytes + pinned_bytes / 4;
+    }
+    *out = &sc;
+    return 0;
+}
+}  // namespace
 
 int h263cu_yuv420_to_rgba(const uint8_t* y, const uint8_t* chroma_b, const uint8_t* chroma_r, size_t y_len,
                           size_t y_width, uint8_t* rgba_out) {
@@ -813,14 +1049,19 @@ int h263cu_yuv420_to_rgba(const uint8_t* y, const uint8_t* chroma_b, const uint8
     std::lock_guard<std::mutex> lock(g_scratch_mutex);
     const size_t h = y_len / y_width, cw = (y_width + 1) / 2, ch = (h + 1) / 2, clen = cw * ch;
     const size_t o_cb = round_up(y_len, 256), o_cr = o_cb + round_up(clen, 256), o_out = o_cr + round_up(clen, 256);
-    int e = scratch_reserve(o_out + y_len * 4);
+    DropInScratch* sc;
+    int e = scratch_get(o_out + y_len * 4, o_out + y_len * 4, &sc);
     if (e) return e;
-    CU_TRY(cudaMemcpy(g_scratch, y, y_len, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(g_scratch + o_cb, chroma_b, clen, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(g_scratch + o_cr, chroma_r, clen, cudaMemcpyHostToDevice));
-    launch_yuv420_to_rgba(g_scratch, g_scratch + o_cb, g_scratch + o_cr, (uint32_t)y_width, (uint32_t)h, g_scratch + o_out, 0);
+    // pinned staging in both directions: one asynchronous copy each way on the drop-ins' own stream
+    std::memcpy(sc->pinned, y, y_len);
+    std::memcpy(sc->pinned + o_cb, chroma_b, clen);
+    std::memcpy(sc->pinned + o_cr, chroma_r, clen);
+    CU_TRY(cudaMemcpyAsync(sc->dev, sc->pinned, o_cr + clen, cudaMemcpyHostToDevice, sc->stream));
+    launch_yuv420_to_rgba(sc->dev, sc->dev + o_cb, sc->dev + o_cr, (uint32_t)y_width, (uint32_t)h, sc->dev + o_out, sc->stream);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpy(rgba_out, g_scratch + o_out, y_len * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpyAsync(sc->pinned + o_out, sc->dev + o_out, y_len * 4, cudaMemcpyDeviceToHost, sc->stream));
+    CU_TRY(cudaStreamSynchronize(sc->stream));
+    std::memcpy(rgba_out, sc->pinned + o_out, y_len * 4);
     return 0;
 }
 
@@ -831,12 +1072,16 @@ int h263cu_deblock(const uint8_t* data, size_t len, size_t width, uint8_t streng
     std::lock_guard<std::mutex> lock(g_scratch_mutex);
     const size_t h = len / width;
     const size_t o_out = round_up(len, 256);
-    int e = scratch_reserve(o_out + len);
+    DropInScratch* sc;
+    int e = scratch_get(o_out + len, o_out + len, &sc);
     if (e) return e;
-    CU_TRY(cudaMemcpy(g_scratch, data, len, cudaMemcpyHostToDevice));
-    launch_deblock_plane(g_scratch, g_scratch + o_out, (uint32_t)width, (uint32_t)h, strength, 0);
+    std::memcpy(sc->pinned, data, len);
+    CU_TRY(cudaMemcpyAsync(sc->dev, sc->pinned, len, cudaMemcpyHostToDevice, sc->stream));
+    launch_deblock_plane(sc->dev, sc->dev + o_out, (uint32_t)width, (uint32_t)h, strength, sc->stream);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpy(out, g_scratch + o_out, len, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpyAsync(sc->pinned + o_out, sc->dev + o_out, len, cudaMemcpyDeviceToHost, sc->stream));
+    CU_TRY(cudaStreamSynchronize(sc->stream));
+    std::memcpy(out, sc->pinned + o_out, len);
     return 0;
 }
 

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <pthread.h>
 #include <thread>
 #include <vector>
@@ -41,12 +42,25 @@ void VlcTable::build(const VlcCode* codes, int n) {
 namespace {
 struct Tables {
     VlcTable t[5];
+    // TCOEF again, laid out for the event loop: one word per 12-bit prefix =
+    //   len[4:0] | kind[6:5] | last[7] | (run << 10 | level)[31:16]   (level > 0: the sign bit follows the code)
+    // so that code, sign and the packed narrow event unit come from one load
+    std::vector<uint32_t> tcoef_fast;
+    int tcoef_bits = 0;
     Tables() {
         t[T_MCBPC_I].build(MCBPC_I_CODES, MCBPC_I_CODES_COUNT);
         t[T_MCBPC_P].build(MCBPC_P_CODES, MCBPC_P_CODES_COUNT);
         t[T_CBPY].build(CBPY_CODES, CBPY_CODES_COUNT);
         t[T_MVD].build(MVD_CODES, MVD_CODES_COUNT);
         t[T_TCOEF].build(TCOEF_CODES, TCOEF_CODES_COUNT);
+        tcoef_bits = t[T_TCOEF].max_len;
+        tcoef_fast.resize(t[T_TCOEF].lut.size());
+        for (size_t i = 0; i < tcoef_fast.size(); i++) {
+            const VlcEntry& e = t[T_TCOEF].lut[i];
+            uint32_t w = e.len() | (e.kind() << 5);
+            if (e.kind() == 0) w |= ((uint32_t)(e.a != 0) << 7) | ((((uint32_t)e.b << 10) | (uint32_t)e.c) << 16);
+            tcoef_fast[i] = w;
+        }
     }
 };
 const Tables& tables() {
@@ -56,6 +70,10 @@ const Tables& tables() {
 }  // namespace
 
 const VlcTable& vlc_table(int id) { return tables().t[id]; }
+static const uint32_t* tcoef_fast_table(int* bits) {
+    *bits = tables().tcoef_bits;
+    return tables().tcoef_fast.data();
+}
 const VlcCode* vlc_codes(int id, int* count) {
     switch (id) {
         case T_MCBPC_I: *count = MCBPC_I_CODES_COUNT; return MCBPC_I_CODES;
@@ -250,6 +268,14 @@ struct h263cu_parser {
     std::vector<h263cu_event> st_events;
     h263cu_pic st_pic;
     int st_err = 0;
+    // stream state after the picture parsed last by a deferred-commit parse step (h263fe::parse_step_deferred);
+    // it becomes the parser's state only when the device stage has accepted the step
+    struct Pending {
+        bool valid = false;
+        bool has_last = false, has_reference = false;
+        int fmt_kind = -1;
+        uint16_t w = 0, h = 0;
+    } pending;
 };
 
 namespace {
@@ -323,14 +349,87 @@ static inline int parse_block(BitReader& r_io, const Header& hd, uint32_t option
     return 0;
 }
 
+// One block, the fast form (block.rs:670-755): events are written straight into the output as narrow units
+// (RUN << 10 | LEVEL as a signed 10-bit field); *wide is set when some level does not fit, and the caller then
+// re-reads the macroblock with parse_block (rare: Sorenson 11-bit escapes beyond +-511).  The reader is a local of the
+// caller whose address never escapes, so the bit window stays in registers across the stores.
+// A block whose runs overflow the zig-zag is dropped (*nev = 0, rle.rs:125-127) but still parsed to its end.
+static H263_AI int parse_block_fast(BitReader& r, const uint32_t* __restrict tf, int tf_bits, bool sorenson_v1, bool intra, bool coded,
+                                    int* dc_code, h263cu_event* __restrict out, int* nev, bool* overflow, bool* wide) {
+    uint32_t v;
+    *dc_code = -1;
+    *nev = 0;
+    *overflow = false;
+    if (intra) {
+        if (!r.read(8, &v)) return H263CU_ERR_UNHANDLED_IO_ERROR;
+        if (v == 0 || v == 128) return H263CU_ERR_INVALID_INTRA_DC;
+        *dc_code = (int)v;
+    }
+    if (!coded) return 0;
+    int idx = intra ? 1 : 0;
+    int n = 0;
+    bool ovf = false;
+    for (;;) {
+        const uint64_t w = r.window();
+        const uint32_t e = tf[(uint32_t)(w >> (64 - tf_bits))];
+        const unsigned len = e & 31u, kind = (e >> 5) & 3u;
+        int last, run, level;
+        uint32_t unit;
+        if (__builtin_expect(kind == 0, 1)) {
+            if (__builtin_expect(len + 1 > r.avail(), 0)) return H263CU_ERR_UNHANDLED_IO_ERROR;  // code, then its sign bit
+            const uint32_t sign = (uint32_t)((w << len) >> 63);
+            r.consume(len + 1);
+            last = (int)((e >> 7) & 1u);
+            unit = e >> 16;
+            run = (int)(unit >> 10);
+            // negate the 10-bit level field when the sign bit is set
+            unit = (unit & 0xFC00u) | ((((unit & 0x3FFu) ^ (0u - sign)) + sign) & 0x3FFu);
+        } else if (kind == 3) {
+            if (len > r.avail()) return H263CU_ERR_UNHANDLED_IO_ERROR;
+            r.consume(len);
+            unsigned width = 8;
+            if (sorenson_v1) {
+                if (!r.read(1, &v)) return H263CU_ERR_UNHANDLED_IO_ERROR;
+                width = v ? 11 : 7;
+            }
+            uint32_t l, rn;
+            int32_t lv;
+            if (!r.read(1, &l) || !r.read(6, &rn) || !r.read_signed(width, &lv)) return H263CU_ERR_UNHANDLED_IO_ERROR;
+            if (lv == 0) return H263CU_ERR_INVALID_LONG_COEFFICIENT;
+            last = (int)l, run = (int)rn, level = lv;
+            *wide |= level < -512 || level > 511;
+            unit = ((uint32_t)run << 10) | ((uint32_t)level & 0x3FFu);
+        } else {
+            if (len > r.avail()) return H263CU_ERR_UNHANDLED_IO_ERROR;
+            return H263CU_ERR_INVALID_SHORT_COEFFICIENT;
+        }
+        idx += run;
+        ovf |= idx >= 64;
+        out[n] = (h263cu_event)unit;  // the caller leaves room for 64 units per block
+        n += ovf ? 0 : 1;
+        idx += 1;
+        if (last) break;
+    }
+    *overflow = ovf;
+    *nev = ovf ? 0 : n;
+    return 0;
+}
+
 // The serial loop of decode_next_picture (state.rs:142-427) for one packet.
 static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len, uint32_t stream, uint16_t pic_index,
                               uint32_t mb_base, uint32_t ev_base, h263cu_pic* pic, h263cu_mb* mbs, uint32_t mb_cap,
                               h263cu_event* events, uint32_t ev_cap, PendingState* pending) {
-    BitReader r(data, len);
+    BitReader r0(data, len);
     Header hd;
-    int e = parse_header(r, p->options, p->has_last, p->last_fmt_kind, p->last_w, p->last_h, &hd);
+    int e = parse_header(r0, p->options, p->has_last, p->last_fmt_kind, p->last_w, p->last_h, &hd);
     if (e) return e;
+    // The macroblock loop works on its own copy of the reader, every use of which is inlined: its address never
+    // escapes, so the 64-bit window stays in registers across the byte stores into the records (which may alias
+    // anything the compiler cannot prove local).  Out-of-line helpers get a copy.
+    BitReader r = r0;
+    int tf_bits;
+    const uint32_t* const tf = tcoef_fast_table(&tf_bits);
+    const bool sorenson_v1 = (p->options & H263CU_OPT_SORENSON_SPARK_BITSTREAM) && hd.version == 1;
     if (!hd.dims_valid) return H263CU_ERR_PICTURE_FORMAT_INVALID;
     const uint32_t W = hd.w, H = hd.h;
     const uint32_t mb_w = (W + 15) / 16, mb_h = (H + 15) / 16;
@@ -341,15 +440,20 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
 
     const bool is_sorenson = (p->options & H263CU_OPT_SORENSON_SPARK_BITSTREAM) != 0;
     const bool is_i = hd.pic_type == H263CU_PIC_I;
-    const VlcTable& TM = vlc_table(is_i ? T_MCBPC_I : T_MCBPC_P);
-    const VlcTable& TC = vlc_table(T_CBPY);
-    const VlcTable& TV = vlc_table(T_MVD);
+    const VlcTable& TMt = vlc_table(is_i ? T_MCBPC_I : T_MCBPC_P);
+    const VlcTable& TCt = vlc_table(T_CBPY);
+    const VlcTable& TVt = vlc_table(T_MVD);
+    const VlcEntry* const TM = TMt.lut.data();
+    const VlcEntry* const TC = TCt.lut.data();
+    const VlcEntry* const TV = TVt.lut.data();
+    const unsigned TM_len = (unsigned)TMt.max_len, TC_len = (unsigned)TCt.max_len, TV_len = (unsigned)TVt.max_len;
 
     p->mvs.assign((size_t)capacity * 4, Mv{0, 0});
     Mv* mvs = p->mvs.data();
 
     int quant = hd.quant;
     uint32_t n = 0;        // macroblocks decoded so far (may exceed capacity with trailing COD=1 bits)
+    uint32_t col = 0, row = 0;  // = n % mb_w, n / mb_w, kept by increments
     uint32_t ev_used = 0;  // event units written
     bool any_inter = false;
     bool mv_in_range = true;  // halfpel_decode wraps every component into [-32, 31] (mvd_pred.rs:70-117); checked anyway
@@ -387,7 +491,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                 break;
             }
             const VlcEntry* en;
-            if (!r.read_vlc(TM, &en)) {
+            if (!r.read_vlc(TM, TM_len, &en)) {
                 err = H263CU_ERR_UNHANDLED_IO_ERROR;
                 break;
             }
@@ -401,7 +505,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
             }
             mb_type = en->a;
             cbp[4] = en->b != 0, cbp[5] = en->c != 0;
-            if (!r.read_vlc(TC, &en)) {
+            if (!r.read_vlc(TC, TC_len, &en)) {
                 err = H263CU_ERR_UNHANDLED_IO_ERROR;
                 break;
             }
@@ -424,7 +528,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                 int nmv = (mb_type == 2 || mb_type == 5) ? 4 : 1;
                 for (int k = 0; k < nmv && !err; k++) {
                     for (int c = 0; c < 2; c++) {
-                        if (!r.read_vlc(TV, &en)) {
+                        if (!r.read_vlc(TV, TV_len, &en)) {
                             err = H263CU_ERR_UNHANDLED_IO_ERROR;
                             break;
                         }
@@ -445,7 +549,8 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                 !is_sorenson) {
                 // GOB resynchronisation stub (state.rs:387-408, gob.rs:50-71)
                 uint32_t skipped = 0;
-                int ge = find_start_code(r, &skipped);
+                BitReader probe = r;
+                int ge = find_start_code(probe, &skipped);
                 if (ge == H263CU_ERR_MIDDLE_OF_BITSTREAM) break;  // InvalidGobHeader ends the picture
                 if (ge) break;                                    // EOF ends the picture
                 if (r.avail() < 17 + skipped + 5) break;          // EOF while reading the GOB number
@@ -467,12 +572,13 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                 std::memset(&m, 0, sizeof(m));
                 m.ev_off = ev_used;
                 m.pic = pic_index;
-                m.mbx = (uint8_t)(n % mb_w), m.mby = (uint8_t)(n / mb_w);
+                m.mbx = (uint8_t)col, m.mby = (uint8_t)row;
                 m.flags = H263CU_MB_INTER;
                 m.quant = (uint8_t)quant;
                 any_inter = true;
             }
             n++;
+            if (++col == mb_w) col = 0, row++;
             continue;
         }
 
@@ -484,10 +590,10 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
             // errors win) and then indexes past its coefficient array and aborts (rle.rs:89-90).
             int dc, nev0;
             bool ovf;
-            int be = parse_block(r, hd, p->options, intra, cbp[0], &dc, ev_run[0], ev_level[0], &nev0, &ovf);
+            BitReader tmp = r;
+            int be = parse_block(tmp, hd, p->options, intra, cbp[0], &dc, ev_run[0], ev_level[0], &nev0, &ovf);
             return be ? be : H263CU_ERR_REFERENCE_WOULD_ABORT;
         }
-        const uint32_t col = n % mb_w, row = n / mb_w;
         Mv* cur = mvs + (size_t)n * 4;
         if (!intra) {
             const bool four = mb_type == 2 || mb_type == 5;
@@ -530,36 +636,65 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                             ((mb_type == 2 || mb_type == 5) ? H263CU_MB_FOURMV : 0));
         int nev[6];
         bool wide = false;
-        for (int b = 0; b < 6; b++) {
-            int dc;
-            bool ovf;
-            int be = parse_block(r, hd, p->options, intra, cbp[b], &dc, ev_run[b], ev_level[b], &nev[b], &ovf);
+        uint32_t units = 0;
+        if (ev_cap - ev_used >= 6 * 65) {
+            // fast path: narrow units straight into the output (a block writes at most 65 units before it stops counting)
+            const size_t blocks_start = r.pos();
+            h263cu_event* ev = events + ev_used;
+            int be = 0;
+            for (int b = 0; b < 6 && !be; b++) {
+                int dc;
+                bool ovf;
+                be = parse_block_fast(r, tf, tf_bits, sorenson_v1, intra, cbp[b], &dc, ev, &nev[b], &ovf, &wide);
+                if (intra) m.u.intradc[b] = ovf ? 0 : (uint8_t)dc;
+                m.nev[b] = (uint8_t)nev[b];
+                ev += nev[b];
+            }
             if (be) return be;  // `?`: block errors, EOF included, fail the whole picture
-            if (intra) m.u.intradc[b] = ovf ? 0 : (uint8_t)dc;
-            m.nev[b] = (uint8_t)nev[b];
-            for (int k = 0; k < nev[b]; k++) wide |= ev_level[b][k] < -512 || ev_level[b][k] > 511;
+            if (!wide) {
+                units = (uint32_t)(ev - (events + ev_used));
+            } else {
+                r.seek(blocks_start);  // some level needs 16 bits: read the macroblock again in the wide form
+            }
+        } else {
+            wide = true;  // almost out of room: take the careful path, which checks the capacity exactly
+        }
+        if (wide) {
+            wide = false;
+            BitReader tmp = r;
+            for (int b = 0; b < 6; b++) {
+                int dc;
+                bool ovf;
+                int be = parse_block(tmp, hd, p->options, intra, cbp[b], &dc, ev_run[b], ev_level[b], &nev[b], &ovf);
+                if (be) return be;
+                if (intra) m.u.intradc[b] = ovf ? 0 : (uint8_t)dc;
+                m.nev[b] = (uint8_t)nev[b];
+                for (int k = 0; k < nev[b]; k++) wide |= ev_level[b][k] < -512 || ev_level[b][k] > 511;
+            }
+            r = tmp;
+            uint32_t total = 0;
+            for (int b = 0; b < 6; b++) total += (uint32_t)nev[b];
+            units = wide ? total * 2 : total;
+            if (ev_used + units > ev_cap) return H263CU_ERR_CAPACITY;
+            h263cu_event* ev = events + ev_used;
+            if (wide) {
+                m.flags |= H263CU_MB_WIDE;
+                for (int b = 0; b < 6; b++)
+                    for (int k = 0; k < nev[b]; k++) {
+                        *ev++ = ev_run[b][k];
+                        *ev++ = (uint16_t)ev_level[b][k];
+                    }
+            } else {
+                for (int b = 0; b < 6; b++)
+                    for (int k = 0; k < nev[b]; k++)
+                        *ev++ = (uint16_t)(((uint32_t)ev_run[b][k] << 10) | ((uint32_t)ev_level[b][k] & 0x3FF));
+            }
         }
         if (!intra)
             for (int k = 0; k < 4; k++) m.u.mv[k][0] = cur[k].x, m.u.mv[k][1] = cur[k].y;
-        uint32_t total = 0;
-        for (int b = 0; b < 6; b++) total += (uint32_t)nev[b];
-        uint32_t units = wide ? total * 2 : total;
-        if (ev_used + units > ev_cap) return H263CU_ERR_CAPACITY;
-        h263cu_event* ev = events + ev_used;
-        if (wide) {
-            m.flags |= H263CU_MB_WIDE;
-            for (int b = 0; b < 6; b++)
-                for (int k = 0; k < nev[b]; k++) {
-                    *ev++ = ev_run[b][k];
-                    *ev++ = (uint16_t)ev_level[b][k];
-                }
-        } else {
-            for (int b = 0; b < 6; b++)
-                for (int k = 0; k < nev[b]; k++)
-                    *ev++ = (uint16_t)(((uint32_t)ev_run[b][k] << 10) | ((uint32_t)ev_level[b][k] & 0x3FF));
-        }
         ev_used += units;
         n++;
+        if (++col == mb_w) col = 0, row++;
     }
 
     // A picture that ended early is padded with uncoded inter MBs (state.rs:419-427)
@@ -731,12 +866,15 @@ int h263cu_parse_picture(h263cu_parser* p, const uint8_t* data, size_t len, uint
     return 0;
 }
 
-int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
-                      const uint32_t* stream_ids, uint32_t n, int threads, h263cu_pic* pics, h263cu_mb* mbs,
-                      uint32_t mb_cap, h263cu_event* events, uint32_t ev_cap, uint32_t* n_pics_out,
-                      uint32_t* n_mbs_out, uint32_t* n_units_out, int* per_pic_err, int32_t* pic_of_input) {
+static int parse_step_impl(h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                           const uint32_t* stream_ids, uint32_t n, int threads, h263cu_pic* pics, h263cu_mb* mbs,
+                           uint32_t mb_cap, h263cu_event* events, uint32_t ev_cap, uint32_t* n_pics_out,
+                           uint32_t* n_mbs_out, uint32_t* n_units_out, int* per_pic_err, int32_t* pic_of_input,
+                           bool commit_now, uint32_t max_w, uint32_t max_h) {
     if (!parsers || !packets || !lens || !pics || !mbs || !n_pics_out || !n_mbs_out || !n_units_out)
         return H263CU_ERR_BAD_ARGUMENT;
+    for (uint32_t i = 0; i < n; i++)
+        if (parsers[i]) parsers[i]->pending.valid = false;
     if (n > 65535) return H263CU_ERR_CAPACITY;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     threads = (int)std::min<uint32_t>((uint32_t)threads, std::max(1u, n));
@@ -749,13 +887,27 @@ int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packe
             uint32_t i = next.fetch_add(1);
             if (i >= n) break;
             h263cu_parser* p = parsers[i];
+            if (!p) continue;  // reported as H263CU_ERR_BAD_ARGUMENT below
+            int e = 0;
             h263cu_pic hdr;
-            int e = h263cu_peek_picture(p->options, packets[i], lens[i], &hdr);
+            if (!packets[i]) e = H263CU_ERR_BAD_ARGUMENT;
+            if (!e) e = h263cu_peek_picture(p->options, packets[i], lens[i], &hdr);
             if (!e && hdr.n_mbs == 0) e = H263CU_ERR_PICTURE_FORMAT_INVALID;
+            // a hostile header (Sorenson's 16-bit custom size) must not size the staging: more than 255 macroblocks
+            // per row / column cannot be described by a record, and a picture beyond the context is this picture's
+            // error, not the step's
+            if (!e && ((hdr.width + 15u) / 16u > 255u || (hdr.height + 15u) / 16u > 255u)) e = H263CU_ERR_CAPACITY;
+            if (!e && max_w && (hdr.width > max_w || hdr.height > max_h)) e = H263CU_ERR_CAPACITY;
             if (!e) {
-                p->st_mbs.resize(hdr.n_mbs);
-                // every event costs at least 3 bits and takes at most 2 units (wide MBs)
-                p->st_events.resize(lens[i] * 16 / 3 + 16);
+                try {
+                    p->st_mbs.resize(hdr.n_mbs);
+                    // every event costs at least 3 bits and takes at most 2 units (wide MBs)
+                    p->st_events.resize(lens[i] * 16 / 3 + 16);
+                } catch (const std::bad_alloc&) {
+                    e = H263CU_ERR_OUT_OF_MEMORY;
+                }
+            }
+            if (!e) {
                 e = parse_picture_impl(p, packets[i], lens[i], stream_ids ? stream_ids[i] : i, 0, 0, 0, &p->st_pic,
                                        p->st_mbs.data(), (uint32_t)p->st_mbs.size(), p->st_events.data(),
                                        (uint32_t)p->st_events.size(), &pend[i]);
@@ -771,6 +923,10 @@ int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packe
     std::vector<int32_t> packed(n, -1);
     for (uint32_t i = 0; i < n; i++) {
         h263cu_parser* p = parsers[i];
+        if (!p) {
+            if (per_pic_err) per_pic_err[i] = H263CU_ERR_BAD_ARGUMENT;
+            continue;
+        }
         if (per_pic_err) per_pic_err[i] = p->st_err;
         if (p->st_err) continue;
         if ((uint64_t)nm + p->st_pic.n_mbs > mb_cap || (uint64_t)nu + p->st_pic.n_event_units > ev_cap)
@@ -797,7 +953,13 @@ int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packe
             for (uint32_t k = 0; k < pc.n_mbs; k++) dst[k].pic = (uint16_t)packed[i];
             if (pc.n_event_units)
                 std::memcpy(events + ev_base[i], p->st_events.data(), (size_t)pc.n_event_units * sizeof(h263cu_event));
-            commit(p, pend[i]);
+            if (commit_now) {
+                commit(p, pend[i]);
+            } else {
+                p->pending.valid = true;
+                p->pending.has_last = pend[i].has_last, p->pending.has_reference = pend[i].has_reference;
+                p->pending.fmt_kind = pend[i].fmt_kind, p->pending.w = pend[i].w, p->pending.h = pend[i].h;
+            }
         }
     };
     worker_pool().run(threads, work2);
@@ -806,6 +968,18 @@ int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packe
     *n_mbs_out = nm;
     *n_units_out = nu;
     return 0;
+}
+
+int h263cu_parse_step(h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                      const uint32_t* stream_ids, uint32_t n, int threads, h263cu_pic* pics, h263cu_mb* mbs,
+                      uint32_t mb_cap, h263cu_event* events, uint32_t ev_cap, uint32_t* n_pics_out,
+                      uint32_t* n_mbs_out, uint32_t* n_units_out, int* per_pic_err, int32_t* pic_of_input) {
+    try {
+        return parse_step_impl(parsers, packets, lens, stream_ids, n, threads, pics, mbs, mb_cap, events, ev_cap, n_pics_out,
+                               n_mbs_out, n_units_out, per_pic_err, pic_of_input, true, 0, 0);
+    } catch (const std::bad_alloc&) {
+        return H263CU_ERR_OUT_OF_MEMORY;
+    }
 }
 
 // ---- test hooks: the front end's own bit reader, tables and block decoder behind plain C calls, so that the
@@ -912,6 +1086,33 @@ const char* h263cu_strerror(int err) {
 int h263cu_version(void) { return 100; }
 
 }  // extern "C"
+
+// ---- deferred-commit form used by h263cu_decode_step (context.cu): the parsers advance only when the device stage
+// has accepted the step, so that decode_next_picture stays a transaction end to end (state.rs:120-137) ----
+namespace h263fe {
+int parse_step_deferred(h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                        const uint32_t* stream_ids, uint32_t n, int threads, h263cu_pic* pics, h263cu_mb* mbs, uint32_t mb_cap,
+                        h263cu_event* events, uint32_t ev_cap, uint32_t* n_pics_out, uint32_t* n_mbs_out, uint32_t* n_units_out,
+                        int* per_pic_err, int32_t* pic_of_input, uint32_t max_w, uint32_t max_h) {
+    try {
+        return parse_step_impl(parsers, packets, lens, stream_ids, n, threads, pics, mbs, mb_cap, events, ev_cap, n_pics_out,
+                               n_mbs_out, n_units_out, per_pic_err, pic_of_input, false, max_w, max_h);
+    } catch (const std::bad_alloc&) {
+        return H263CU_ERR_OUT_OF_MEMORY;
+    }
+}
+void parse_step_finish(h263cu_parser* const* parsers, uint32_t n, bool accept) {
+    for (uint32_t i = 0; i < n; i++) {
+        h263cu_parser* p = parsers[i];
+        if (!p || !p->pending.valid) continue;
+        if (accept) {
+            p->has_last = p->pending.has_last, p->has_reference = p->pending.has_reference;
+            p->last_fmt_kind = p->pending.fmt_kind, p->last_w = p->pending.w, p->last_h = p->pending.h;
+        }
+        p->pending.valid = false;
+    }
+}
+}  // namespace h263fe
 
 static_assert(sizeof(h263cu_pic) == 32, "h263cu_pic layout");
 static_assert(sizeof(h263cu_mb) == 24, "h263cu_mb layout");

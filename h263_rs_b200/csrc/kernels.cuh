@@ -48,16 +48,16 @@ struct Pools {
 // recon_mb_kernel.
 // tiled: 1 = every picture is a multiple of 16 in size, 2 = some are not (edge fix-up instantiation).
 // wide_mv: some picture of the step may hold vectors beyond [-32, 31] half-pel units (no H263CU_PICFLAG_MV_IN_RANGE).
-// rgba_map: TMA tensor map over the context's RGBA pool (2-D, rows of rgba_pitch bytes, box 64 bytes x 16 rows,
-// 128-byte swizzle): the tiled kernel stores RGBA through it.
+// rgba_map: TMA tensor map over the context's RGBA pool (2-D, rows of rgba_pitch bytes, box 64 bytes x 16 rows):
+// the tiled kernel stores RGBA through it.
 void launch_recon(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
                   int emit_rgba, int tiled, int wide_mv, const Pools& pools, const CUtensorMap* rgba_map, cudaStream_t stream);
 // recon_tile.cu
 void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs,
                        int emit_rgba, int unaligned, int wide_mv, const Pools& pools, const CUtensorMap* rgba_map,
                        cudaStream_t stream);
-// how the tiled kernel stores RGBA: 1 = TMA from a 128B-swizzled tile (the build default), 2 = TMA from a dense tile,
-// 0 = direct global stores (build variants for A/B measurements)
+// how the tiled kernel stores RGBA: 1 = TMA tensor stores from a shared-memory tile (the build default),
+// 0 = direct global stores (build variant for A/B measurements)
 int recon_tile_uses_tma();
 
 // Plane padding (bytes / rows) reserved around every reconstruction plane: the tiled kernel

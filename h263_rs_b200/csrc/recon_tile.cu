@@ -17,7 +17,7 @@
 //            same code as a luma row: two aligned words per prediction row, half-pel
 //            interpolation in 16-bit lanes (gather.rs:34-40,103-113), saturating residual add,
 //            plane stores, border replication, BT.601 RGBA (bt601.rs:12-59).  RGBA leaves through
-//            a 128B-swizzled shared-memory tile and one TMA tensor store per macroblock
+//            a shared-memory tile and one TMA tensor store per macroblock
 //            (cp.async.bulk.tensor.2d), which takes the 415 MB per step of RGBA off the LSU pipe.
 //
 // Four lanes side by side cover a macroblock row, so a prediction pass touches the sectors of 8
@@ -46,10 +46,6 @@ constexpr int WARP_MBS = 4;  // macroblocks per warp
 // 1 = RGBA through the shared-memory tile + TMA tensor stores, 0 = one 128-bit global store per lane and row
 #ifndef H263_RGBA_TMA
 #define H263_RGBA_TMA 1
-#endif
-// 1 = the RGBA tile uses the 128-byte TMA swizzle (conflict-free 128-bit shared stores), 0 = dense rows
-#ifndef H263_RGBA_SWIZZLE
-#define H263_RGBA_SWIZZLE 0
 #endif
 constexpr int CTA_WARPS = H263_CTA_WARPS;
 constexpr int CTA_THREADS = CTA_WARPS * 32;
@@ -94,7 +90,7 @@ struct __align__(16) WarpTail {
 // 8 CTAs x (23.5 + 1) KB fill the 196 KB shared-memory carve-out exactly; one more byte per CTA would take the
 // 228 KB carve-out and leave no L1 (8 % slower, profiles/r01_variants.txt)
 struct TileSmem {
-    WarpStage stage[CTA_WARPS];  // first: every stage is 1024-byte aligned (the TMA swizzle is a function of the address)
+    WarpStage stage[CTA_WARPS];  // first: TMA store sources must be 128-byte aligned
     WarpTail tail[CTA_WARPS];
 };
 static_assert(sizeof(TileSmem) <= 24064 * CTA_WARPS / 4, "shared memory budget of 8 CTAs per SM");
@@ -181,16 +177,13 @@ __device__ __forceinline__ uint32_t merge_bytes(uint32_t a, uint32_t b, int keep
     return (a & m) | (b & ~m);
 }
 
-// Byte offset of (macroblock q, row, 16-byte chunk c) inside the warp's RGBA tile.  Each macroblock is a 16-row x
-// 64-byte box of a TMA store; with CU_TENSOR_MAP_SWIZZLE_128B the 16-byte chunk index (address bits 4..6) is XORed
-// with address bits 7..9, which spreads the two row groups and the row pairs of a pass over all 32 banks.
-__device__ __forceinline__ uint32_t stage_offset(int q, int row, int c) {
-    uint32_t off = (uint32_t)(q * 1024 + row * 64 + c * 16);
-#if H263_RGBA_TMA && H263_RGBA_SWIZZLE
-    off ^= ((off >> 7) & 7u) << 4;
-#endif
-    return off;
-}
+// Byte offset of (macroblock q, row, 16-byte chunk c) inside the warp's RGBA tile.  Each macroblock is a dense
+// 16-row x 64-byte box of a TMA store.  The two row groups of a macroblock write the same banks (rows 8 apart): a 2-way
+// conflict on the eight 128-bit shared stores of a lane.  No TMA swizzle mode removes it for a 64-byte box -- 64B
+// XORs address bits 7..8 only, and 128B pads every 64-byte row to 128 bytes (tools/tma_swizzle_probe.cu,
+// profiles/r02_tma_swizzle_probe.txt) -- and the kernel is not bound by it (direct 128-bit global stores, the dense
+// tile and a conflict-free layout run within 0.5 % of each other, profiles/r02_variants.txt).
+__device__ __forceinline__ uint32_t stage_offset(int q, int row, int c) { return (uint32_t)(q * 1024 + row * 64 + c * 16); }
 
 }  // namespace
 
@@ -500,14 +493,21 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
 #pragma unroll
                     for (int j = 0; j < 8; j++) acc[j] = fadd(acc[j], fmul(a, k_basis(y, j)));
                 }
+                const bool any_vert = __any_sync(FULL, vert);  // warp-uniform, taken outside the lane-dependent branch below
                 if (R) {
-                    // pixel (x = t, y = j): residual row j of the slot, s16 row-major
-                    const float m = vert ? H263_B00 : 1.0f;
+                    // pixel (x = t, y = j): residual row j of the slot, s16 row-major.  The reference clamps the rounded
+                    // value to [-256, 255] (idct.rs:190) before it adds it to the prediction and clamps to [0, 255]
+                    // (idct.rs:191-194); the first clamp cannot change the result of the second (prediction in
+                    // [0, 255]), and |value| <= 2048 * (sum_x |B[x][i]|)^2 / 4 < 14300 fits the s16 that carries it,
+                    // so only the saturating add of phase 3 clamps.
                     uint16_t* rrow = reinterpret_cast<uint16_t*>(&G.res[sl][0]) + t;
+                    if (any_vert) {  // rare: a block with coefficients in its first column only
+                        const float m = vert ? H263_B00 : 1.0f;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int r = round_q(acc[j], m);
-                        rrow[j * 8] = (uint16_t)(int16_t)max(min(r, 255), -256);
+                        for (int j = 0; j < 8; j++) rrow[j * 8] = (uint16_t)(int16_t)round_q(acc[j], m);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) rrow[j * 8] = (uint16_t)(int16_t)__float2int_rz(fadd(acc[j], copysign_half(acc[j])));
                     }
                 }
                 __syncwarp();  // the coefficient slots are reused by the next pass
@@ -827,8 +827,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
     }
 }
 
-// 0 = direct global stores, 1 = TMA stores from a 128B-swizzled tile, 2 = TMA stores from a dense tile
-int recon_tile_uses_tma() { return H263_RGBA_TMA ? (H263_RGBA_SWIZZLE ? 1 : 2) : 0; }
+int recon_tile_uses_tma() { return H263_RGBA_TMA; }
 
 void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs, int emit_rgba,
                        int unaligned, int wide_mv, const Pools& pools, const CUtensorMap* rgba_map, cudaStream_t stream) {

@@ -14,12 +14,27 @@
 #include <map>
 #include <vector>
 
-#include "../../include/h263cu.h"
+#include "../../include/h263synth.h"
 #include "bitio.hpp"
+
+// libh263synth.so stands alone: it carries its own copy of the code tables (the product keeps its copy in frontend.cpp)
+namespace h263fe {
+#include "vlc_codes.inc"
+const VlcCode* vlc_codes(int id, int* count) {
+    switch (id) {
+        case T_MCBPC_I: *count = MCBPC_I_CODES_COUNT; return MCBPC_I_CODES;
+        case T_MCBPC_P: *count = MCBPC_P_CODES_COUNT; return MCBPC_P_CODES;
+        case T_CBPY: *count = CBPY_CODES_COUNT; return CBPY_CODES;
+        case T_MVD: *count = MVD_CODES_COUNT; return MVD_CODES;
+        default: *count = TCOEF_CODES_COUNT; return TCOEF_CODES;
+    }
+}
+}  // namespace h263fe
 
 using namespace h263fe;
 
 namespace {
+constexpr int H263CU_ERR_BAD_ARGUMENT = -100;  // the generator reports errors with the product library's codes
 
 struct Rng {
     uint64_t s;

@@ -209,7 +209,12 @@ void* h263cu_alloc_pinned(size_t bytes);
 void h263cu_free_pinned(void* p);
 
 /* Copy one step's side info into device memory (cudaMemcpyAsync on the context stream) and
- * keep it there: the "inputs resident in HBM" form used for kernel-only timing. */
+ * keep it there: the "inputs resident in HBM" form used for kernel-only timing.
+ * Side info handed in through h263cu_step_upload / h263cu_submit_step / h263cu_submit_step_readback need not come
+ * from the library's parser, so it is checked on the host first: every record must lie in its picture's range, carry
+ * that picture's index, sit at its raster position (mby * mb_w + mbx == index inside the picture) and keep its events
+ * inside the picture's share of the event array, else H263CU_ERR_BAD_ARGUMENT.  H263CU_PICFLAG_HAS_INTER and
+ * H263CU_PICFLAG_MV_IN_RANGE are derived from the records (set / cleared as needed), not taken on trust. */
 h263cu_step* h263cu_step_upload(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
                                 uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, int* err);
 void h263cu_step_free(h263cu_ctx*, h263cu_step*);
@@ -235,15 +240,37 @@ int h263cu_submit_step_readback(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_
  * call returns as soon as the work is queued, so the parse of the next step overlaps this step's
  * kernels and copies.  Pictures that fail to parse are reported in per_pic_err[i] (may be NULL),
  * leave their stream untouched (the reference's transactional behaviour, state.rs:120-137) and are
- * left out of the step; *n_decoded (may be NULL) counts the rest.  What the device stage could refuse
- * (stream id out of range or named twice, picture larger than the context) is checked before any parser
- * advances: such a call fails as a whole and changes nothing.  When host_rgba is not NULL the
+ * left out of the step; *n_decoded (may be NULL) counts the rest.  A picture larger than the context is such a
+ * per-picture error (H263CU_ERR_CAPACITY).  A stream id out of range or named twice fails the call as a whole
+ * before anything is parsed, and the parsers advance only once the device stage has accepted the step: a call
+ * that returns an error has changed no parser and no stream.  When host_rgba is not NULL the
  * RGBA picture of input i is copied to host_rgba + i * rgba_stride (tight rows of 4 * width bytes)
  * on the read-back stream; call h263cu_sync before reading it. */
 int h263cu_decode_step(h263cu_ctx*, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
                        const uint32_t* stream_ids, uint32_t n, int threads, uint32_t out_flags, uint8_t* host_rgba,
                        uint64_t rgba_stride, int* per_pic_err, uint32_t* n_decoded);
 int h263cu_sync(h263cu_ctx*);
+/* Waits for the RGBA read-back of an earlier step only: age 0 = the step submitted last with a read-back, 1 = the one
+ * before it (the read-back ring is two deep).  Lets a caller consume picture t while picture t + 1 is in flight: the
+ * pipelined form of decode_next_picture + yuv420_to_rgba for ONE stream (api.H263State(pipelined=True)). */
+int h263cu_readback_wait(h263cu_ctx*, uint32_t age);
+
+/* ---- one process, several GPUs (streams shard by stream, no exchange between devices) ------------------------------
+ * A group owns one context per listed device and feeds them all from ONE shared pool of parser threads: the pictures
+ * of device d are parsed on all threads and queued on d, then the threads move on to d + 1 while d reconstructs and
+ * copies back.  Global stream s lives on device s % n_devices in slot s / n_devices.  With host_rgba != NULL the RGBA
+ * of stream s lands at host_rgba + ((s % n_devices) * streams_per_device + s / n_devices) * rgba_stride (device-major:
+ * each device's pictures are contiguous).  Errors and the transactional behaviour are those of h263cu_decode_step. */
+typedef struct h263cu_group h263cu_group;
+h263cu_group* h263cu_group_create(const int* devices, uint32_t n_devices, uint32_t streams_per_device, uint32_t max_width,
+                                  uint32_t max_height, int threads, int* err);
+void h263cu_group_destroy(h263cu_group*);
+uint32_t h263cu_group_size(const h263cu_group*);
+h263cu_ctx* h263cu_group_ctx(h263cu_group*, uint32_t index);
+int h263cu_group_decode_step(h263cu_group*, h263cu_parser* const* parsers, const uint8_t* const* packets, const size_t* lens,
+                             const uint32_t* stream_ids, uint32_t n, uint32_t out_flags, uint8_t* host_rgba, uint64_t rgba_stride,
+                             int* per_pic_err, uint32_t* n_decoded);
+int h263cu_group_sync(h263cu_group*);
 
 /* DecodedPicture accessors (h263/src/decoder/picture.rs:60-142): tight row-major planes,
  * chroma = ceil(w/2) x ceil(h/2).  Synchronise the context first. */
@@ -308,37 +335,8 @@ int64_t h263cu_flv_scan(const uint8_t* data, size_t len, h263cu_flv_packet* out,
 int64_t h263cu_flv_mux(const uint8_t* packets, const uint64_t* pkt_off, const uint32_t* pkt_len, const uint8_t* frame_types,
                        uint32_t n, uint32_t ms_per_picture, uint32_t filler_every, uint8_t* out, size_t cap);
 
-/* ---- synthetic Sorenson-flavour bitstream generator (the repo has no encoder) ---------- */
-typedef struct h263cu_synth_params {
-    uint32_t width, height;
-    uint32_t n_pictures;
-    uint64_t seed;
-    uint32_t flavour;      /* 0 = Sorenson Spark, 1 = baseline H.263 (standard sizes only) */
-    uint32_t version;      /* Sorenson version field: 0 or 1 (1 = 7/11-bit escapes) */
-    uint32_t intra_period; /* an I picture every N pictures; 0 = only the first */
-    uint32_t deblock_flag; /* value of the Sorenson DeblockingFlag */
-    uint32_t qp_min, qp_max;
-    uint32_t pct_uncoded;  /* P pictures: % of MBs with COD=1 */
-    uint32_t pct_intra;    /* P pictures: % of MBs coded INTRA */
-    uint32_t pct_fourmv;   /* P pictures: % of MBs coded INTER4V */
-    uint32_t pct_dquant;   /* % of coded MBs carrying DQUANT */
-    uint32_t pct_cbp_inter; /* % of blocks of an inter MB that carry coefficients */
-    uint32_t pct_cbp_intra; /* % of blocks of an intra MB that carry AC coefficients */
-    uint32_t mean_events_x10; /* mean TCOEF events per coded block, times 10 */
-    uint32_t pct_escape;   /* % of events forced through the ESCAPE path */
-    uint32_t permille_overflow; /* per-mille of coded blocks whose runs overflow the zig-zag */
-    uint32_t mv_mode;      /* 0 small vectors, 1 full range uniform, 2 biased across borders */
-    uint32_t truncate_permille; /* per-mille of P pictures that end early (padding path) */
-    uint32_t reserved[4];
-} h263cu_synth_params;
-
-void h263cu_synth_default_params(h263cu_synth_params* p, uint32_t width, uint32_t height, uint32_t n_pictures,
-                                 uint64_t seed);
-/* Writes the stream's packets back to back into out (one byte-aligned, zero-padded packet
- * per picture) and their offsets/lengths; returns the number of bytes needed (call with
- * cap = 0 to size the buffer) or a negative error. */
-int64_t h263cu_synth_stream(const h263cu_synth_params* p, uint8_t* out, size_t cap, uint64_t* pkt_off,
-                            uint32_t* pkt_len);
+/* The synthetic stream generator lives in its own library (include/h263synth.h, libh263synth.so): it is test and
+ * benchmark tooling, not part of the decode path. */
 
 #ifdef __cplusplus
 }

