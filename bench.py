@@ -349,7 +349,7 @@ def run_ours(args, rank, world, local_rank, dist):
     if not args.skip_extras:
         n_check = min(U, 4 if world == 1 else 2)
         mine = parity_check(ctx, blobs, total, n_check)
-        parts = shard.gather_to_rank0(dist, np.array([int(mine["bit_exact_vs_oracle"]), n_check], np.uint64), world, rank)
+        parts = shard.gather_to_rank0(dist, np.array([int(mine["bit_exact_vs_oracle"]), n_check], np.uint64), world, rank, "cuda")
         if rank == 0:
             parity = {"streams_checked_per_rank": n_check, "pictures_each": total, "ranks": world,
                       "bit_exact_vs_oracle_per_rank": [bool(p[0]) for p in parts],
@@ -649,6 +649,14 @@ def single_stream(api, frontend, device):
     pipe_s = time.perf_counter() - t0
     pipe_ok = bool(np.array_equal(last, rgba))
     pipe_fps = (n - 20) / pipe_s
+    # the same through the C ABI from native code (tools/single_stream_bench.cpp): what a Rust / C caller gets
+    native = None
+    try:
+        exe = os.path.join(ROOT, "h263_rs_b200", "single_stream_bench.bin")
+        r = subprocess.run([exe, os.path.join(ROOT, "h263_rs_b200"), str(device)], capture_output=True, text=True, timeout=120)
+        native = json.loads(r.stdout) if r.returncode == 0 else {"error": r.stderr[-300:]}
+    except Exception as e:  # the tool is optional evidence, never a reason to lose the bench line
+        native = {"error": repr(e)}
     sync_fps, cpu_fps = (n - 20) / sync_s, (n - 20) / cpu_s
     return {"frames_per_s": fps, "value": fps * W * H / 1e6, "unit": UNIT, "pictures": n,
             "note": "one dependent kernel launch per picture (396 macroblocks): latency bound, not a roofline case",
@@ -660,6 +668,7 @@ def single_stream(api, frontend, device):
                               "last_picture_matches_synchronous": pipe_ok,
                               "path": "H263State(pipelined=True): decode_next_picture(packet t+1) queued before picture t's RGBA is "
                                       "consumed (h263cu_readback_wait), two pinned buffers alternate, Python caller"},
+            "native_c_abi": native,
             "cpu_port_one_core": {"frames_per_s": cpu_fps, "value": cpu_fps * W * H / 1e6, "unit": UNIT,
                                   "note": "oracle (C++ restatement of h263-rs) on one host core, same packets, planes + RGBA"}}
 

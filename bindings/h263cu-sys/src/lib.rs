@@ -197,6 +197,7 @@ extern "C" {
         c: *mut h263cu_ctx, stream: u32, width: *mut u32, height: *mut u32, pic_type: *mut u32, pquant: *mut u32,
         temporal_reference: *mut u32,
     ) -> c_int;
+    pub fn h263cu_stream_dims(c: *mut h263cu_ctx, stream: u32) -> u32;
     pub fn h263cu_read_yuv(c: *mut h263cu_ctx, stream: u32, y: *mut u8, cb: *mut u8, cr: *mut u8) -> c_int;
     pub fn h263cu_read_rgba(c: *mut h263cu_ctx, stream: u32, rgba: *mut u8) -> c_int;
     pub fn h263cu_checksums(c: *mut h263cu_ctx, streams: *const u32, n: u32, out4: *mut u64) -> c_int;

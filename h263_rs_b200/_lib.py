@@ -63,7 +63,7 @@ SYMBOLS = [
     "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength",
     "h263cu_flv_scan", "h263cu_flv_mux",
     "h263cu_test_read_bits", "h263cu_test_start_code", "h263cu_test_read_vlc", "h263cu_test_decode_block",
-    "h263cu_readback_wait", "h263cu_group_create", "h263cu_group_destroy", "h263cu_group_size", "h263cu_group_ctx",
+    "h263cu_readback_wait", "h263cu_stream_dims", "h263cu_group_create", "h263cu_group_destroy", "h263cu_group_size", "h263cu_group_ctx",
     "h263cu_group_decode_step", "h263cu_group_sync",
 ]
 
@@ -117,6 +117,8 @@ def lib():
         L.h263cu_decode_step.argtypes = [vp, vp, vp, vp, vp, u32, i32, u32, vp, u64, vp, C.POINTER(u32)]
         L.h263cu_sync.argtypes = [vp]
         L.h263cu_readback_wait.argtypes = [vp, u32]
+        L.h263cu_stream_dims.restype = u32
+        L.h263cu_stream_dims.argtypes = [vp, u32]
         L.h263cu_group_create.restype = vp
         L.h263cu_group_create.argtypes = [vp, u32, u32, u32, u32, i32, C.POINTER(i32)]
         L.h263cu_group_destroy.argtypes = [vp]

@@ -225,6 +225,8 @@ class H263State:
         self.device = device
         self.pipelined = pipelined
         self._ring, self._ring_size, self._ring_pos, self._pending = [None, None], 0, 0, False
+        self._last_dims = (0, 0)
+        self._views, self._views_size = [None, None], -1
         self.parser = frontend.Parser(decoder_options)
         self.ctx = None
         self.out_flags = _lib.OUT_RGBA | (_lib.OUT_DEBLOCK if deblock else 0)
@@ -240,22 +242,27 @@ class H263State:
     def is_sorenson(self):
         return bool(self.decoder_options & SORENSON_SPARK_BITSTREAM)
 
-    def decode_next_picture(self, packet):
+    def decode_next_picture(self, packet, _force_new_ctx=False):
         """One call into h263cu_decode_step for the one stream: parse into the context's pinned staging, upload,
         reconstruction and the RGBA read-back into this state's pinned buffer, then wait.  Transactional like the
         reference (state.rs:120-137): a packet that fails to parse raises and leaves parser and stream untouched."""
-        data = bytes(packet)
+        data = packet if isinstance(packet, bytes) else bytes(packet)
         buf = np.frombuffer(data, np.uint8)
-        hdr = frontend.peek_picture(data, self.decoder_options)
-        w, h = int(hdr["width"]), int(hdr["height"])
-        if w == 0 or h == 0:
-            w = h = 16  # no usable size in the header: the parse inside decode_step reports the reference's error
         # A picture larger than the context needs a bigger one.  It replaces the old context only once the packet has
         # decoded (a size change can only succeed on an I picture, which needs no reference planes): a packet that
-        # fails leaves parser, context and last picture as they were (state.rs:120-137).
+        # fails leaves parser, context and last picture as they were (state.rs:120-137).  With a context in place the
+        # header is not peeked first: decode_step reports a picture that does not fit (H263CU_ERR_CAPACITY) and the
+        # call is repeated with a larger context.
         ctx = self.ctx
-        if ctx is None or w > ctx.max_width or h > ctx.max_height:
-            ctx = Context(self.device, 1, max(w, 16), max(h, 16))
+        if ctx is not None and not _force_new_ctx:
+            w, h = self._last_dims
+        else:
+            hdr = frontend.peek_picture(data, self.decoder_options)
+            w, h = int(hdr["width"]), int(hdr["height"])
+            if w == 0 or h == 0:
+                w = h = 16  # no usable size in the header: the parse inside decode_step reports the reference's error
+            if ctx is None or w > ctx.max_width or h > ctx.max_height:
+                ctx = Context(self.device, 1, max(w, 16), max(h, 16))
         L = _lib.lib()
         size = w * h * 4
         if size > self._ring_size:
@@ -270,18 +277,30 @@ class H263State:
                     self._ring_size = 0
                     raise MemoryError
             self._ring_size = size
+            self._views_size = -1
         pos = self._ring_pos ^ 1  # the buffer that does not hold the last picture
         nd = C.c_uint32(0)
         self._one_packet[0], self._one_len[0], self._one_err[0] = buf.ctypes.data, buf.size, 0
         _lib.check(L.h263cu_decode_step(ctx.h, self._one_parser, self._one_packet, self._one_len, self._one_id.ctypes.data, 1, 1,
                                         self.out_flags, self._ring[pos], 0, self._one_err.ctypes.data, C.byref(nd)))
         if self._one_err[0]:
+            if self._one_err[0] == _lib.ERR_CAPACITY and not _force_new_ctx:
+                return self.decode_next_picture(data, _force_new_ctx=True)  # larger than the context: peek and grow
             raise _lib.H263Error(int(self._one_err[0]))
+        d = L.h263cu_stream_dims(ctx.h, 0)  # the size the parser found (it may differ from the previous picture's)
+        if d != (w << 16 | h):
+            w, h = d >> 16, d & 0xFFFF
+            size = w * h * 4
+            assert size <= self._ring_size  # a picture that fits the context fits the buffers made with it
+        self._last_dims = (w, h)
         if ctx is not self.ctx and self.ctx is not None:
             self.ctx.sync()  # the old context may still be copying the previous picture back
         self.ctx = ctx
         self._ring_pos = pos
-        self._rgba_view = np.ctypeslib.as_array(C.cast(self._ring[pos], C.POINTER(C.c_uint8)), shape=(size,))
+        if self._views_size != size:  # numpy views of the two pinned buffers, made once per picture size
+            self._views = [np.ctypeslib.as_array(C.cast(self._ring[k], C.POINTER(C.c_uint8)), shape=(size,)) for k in range(2)]
+            self._views_size = size
+        self._rgba_view = self._views[pos]
         self._has_picture = True
         self._pending = True
         if not self.pipelined:

@@ -51,8 +51,31 @@ def build_synth(force=False):
     return SYNTH_OUT
 
 
+TOOL_SRC = os.path.join(HERE, "..", "tools", "single_stream_bench.cpp")
+TOOL_OUT = os.path.join(HERE, "single_stream_bench.bin")
+
+
+def build_tools(force=False):
+    """The native single-stream driver bench.py runs for configs[1] (no interpreter in the loop)."""
+    if not force and os.path.exists(TOOL_OUT) and os.path.getmtime(TOOL_OUT) >= max(os.path.getmtime(TOOL_SRC), os.path.getmtime(OUT)):
+        return TOOL_OUT
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-o", TOOL_OUT, TOOL_SRC, "-L", HERE, "-lh263cu", "-Wl,-rpath," + HERE, "-ldl",
+           "-pthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed: " + " ".join(cmd))
+    return TOOL_OUT
+
+
 def build(force=False, verbose=False):
     build_synth(force)
+    out = _build_lib(force, verbose)
+    build_tools(force)
+    return out
+
+
+def _build_lib(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     cmd = nvcc_cmd(["-Xptxas", "-v"] if verbose else [])

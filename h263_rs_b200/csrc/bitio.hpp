@@ -46,21 +46,33 @@ struct BitReader {
     const uint8_t* data;
     size_t total_bits;
 
-    BitReader(const uint8_t* d, size_t len) : data(d), total_bits(len * 8), pos_(0) { refill(); }
-    H263_AI size_t pos() const { return pos_; }
-    H263_AI size_t avail() const { return total_bits - pos_; }
-    H263_AI void seek(size_t p) {
-        pos_ = p;
+    BitReader(const uint8_t* d, size_t len) : data(d), total_bits(len * 8), ptr_(d), end_(d + len), buf_(0), cnt_(0), left_(len * 8) {
         refill();
+    }
+    H263_AI size_t pos() const { return total_bits - left_; }
+    H263_AI size_t avail() const { return left_; }  // kept as a counter: one subtraction per consume
+    H263_AI void seek(size_t p) {
+        ptr_ = data + (p >> 3);
+        buf_ = 0, cnt_ = 0;
+        refill();
+        const unsigned r = (unsigned)(p & 7);  // p <= total_bits: the byte that holds bit p exists whenever r != 0
+        buf_ <<= r;
+        cnt_ -= r;
+        refill();
+        left_ = total_bits - p;
     }
 
     // Next n (<= 32) bits, zero padded past the end of the packet.
-    H263_AI uint32_t peek_padded(unsigned n) const { return n == 0 ? 0u : (uint32_t)(win_ >> (64 - n)); }
-    // The window is rebuilt from memory after every consume: one unaligned 8-byte load + byte swap + shift, no
-    // data-dependent branch (the only branch is the end-of-packet test, taken in the last 8 bytes).  At least 57
-    // bits are valid after every call, so any field or code + sign (<= 32 bits) can be taken from it.
+    H263_AI uint32_t peek_padded(unsigned n) const { return n == 0 ? 0u : (uint32_t)(buf_ >> (64 - n)); }
+    // The buffer is topped up after every consume without a data-dependent branch (the only branch is the
+    // end-of-packet test, taken in the last 8 bytes).  The load address of a refill depends on the PREVIOUS symbol's
+    // length only, so the dependent chain per symbol is shift -> table load -> shift -> or: the 8-byte load and the
+    // byte swap run beside it.  At least 56 bits are valid after every call (fewer only in the packet's last bytes,
+    // where the missing ones read as zeros), so any field or code + sign (<= 32 bits) can be taken from it.
     H263_AI void consume(unsigned n) {
-        pos_ += n;
+        buf_ <<= n;
+        cnt_ -= n;
+        left_ -= n;
         refill();
     }
     H263_AI bool read(unsigned n, uint32_t* out) {
@@ -93,7 +105,7 @@ struct BitReader {
     // The same with the table held by the caller as a raw pointer + width (locals of the caller: no reload of the
     // vector's fields after every store the compiler cannot disambiguate)
     H263_AI bool read_vlc(const VlcEntry* __restrict lut, unsigned max_len, const VlcEntry** out) {
-        const VlcEntry& e = lut[(uint32_t)(win_ >> (64 - max_len))];
+        const VlcEntry& e = lut[(uint32_t)(buf_ >> (64 - max_len))];
         if (e.len() > avail()) return false;
         consume(e.len());
         *out = &e;
@@ -102,7 +114,7 @@ struct BitReader {
     // One VLC symbol followed by `extra` (<= 8) plain bits, fetched from the same window (max_len + extra <= 32).
     // EOF semantics as two separate reads: the code must fit, then the extra bits must fit.
     H263_AI bool read_vlc_bits(const VlcTable& t, unsigned extra, const VlcEntry** out, uint32_t* bits, bool* eof_in_extra) {
-        const uint64_t w = win_;
+        const uint64_t w = buf_;
         const VlcEntry& e = t.lut[(uint32_t)(w >> (64 - t.max_len))];
         const unsigned len = e.len();
         *eof_in_extra = false;
@@ -123,24 +135,30 @@ struct BitReader {
         return true;
     }
     // the window itself, for decoders that look at more than one field per fetch (frontend.cpp's TCOEF loop)
-    H263_AI uint64_t window() const { return win_; }
+    H263_AI uint64_t window() const { return buf_; }
 
   private:
-    size_t pos_;
-    uint64_t win_;  // bits pos_.. MSB-aligned (at least 57 of them), zero padded past the end of the packet
+    const uint8_t* ptr_;  // next byte to fetch
+    const uint8_t* end_;
+    uint64_t buf_;   // the next bits, MSB-aligned; bits below the top cnt_ are either upcoming data or zero
+    unsigned cnt_;   // how many of the top bits are accounted for (fetched and not yet consumed)
+    size_t left_;    // bits of the packet not yet consumed
 
     H263_AI void refill() {
-        const size_t byte = pos_ >> 3, nbytes = total_bits >> 3;
-        uint64_t w;
-        if (__builtin_expect(byte + 8 <= nbytes, 1)) {
+        if (__builtin_expect(ptr_ + 8 <= end_, 1)) {
             uint64_t raw;
-            std::memcpy(&raw, data + byte, 8);
-            w = __builtin_bswap64(raw);
+            std::memcpy(&raw, ptr_, 8);
+            buf_ |= __builtin_bswap64(raw) >> cnt_;
+            ptr_ += (63 - cnt_) >> 3;
+            cnt_ |= 56;
         } else {
-            w = 0;
-            for (size_t i = 0; i < 8; i++) w = (w << 8) | (byte + i < nbytes ? data[byte + i] : 0);
+            // the last bytes of the packet: byte by byte, then zeros
+            buf_ &= cnt_ ? ~0ull << (64 - cnt_) : 0ull;  // drop the look-ahead bits a fast refill may have left below cnt_
+            while (cnt_ <= 56 && ptr_ < end_) {
+                buf_ |= (uint64_t)*ptr_++ << (56 - cnt_);
+                cnt_ += 8;
+            }
         }
-        win_ = w << (pos_ & 7);
     }
 };
 

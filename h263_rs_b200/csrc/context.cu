@@ -193,7 +193,7 @@ void prof_end(h263cu_ctx* c, cudaEvent_t a, cudaEvent_t b, int kind) {
 // (state.rs:464-483: the picture just decoded becomes the reference of the next one).
 // Nothing of the per-stream state changes unless the kernels have been enqueued: a step that is
 // refused, or that fails on the way to the launch, leaves every stream as it was.
-int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
+int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags, bool lean = false) {
     const uint32_t n = (uint32_t)s->pics.size();
     if (n == 0) return 0;
     if (n > 65535) return H263CU_ERR_CAPACITY;  // h263cu_mb.pic is 16 bits wide
@@ -269,10 +269,16 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
         }
     }
     // the descriptors travel on their own stream, so the copy overlaps the previous step's kernels
-    // (pics_done[slot] was waited for above: the kernels that read this ring slot four steps ago are done)
-    CU_TRY(cudaMemcpyAsync(c->d_pics[slot], hp, n * sizeof(PicDev), cudaMemcpyHostToDevice, c->s_pics));
-    CU_TRY(cudaEventRecord(c->pics_up[slot], c->s_pics));
-    CU_TRY(cudaStreamWaitEvent(c->s_main, c->pics_up[slot], 0));
+    // (pics_done[slot] was waited for above: the kernels that read this ring slot four steps ago are done).
+    // Lean form (one small step, e.g. a single stream's picture): everything goes to s_main in order -- there is
+    // nothing to overlap, and every driver call saved is a microsecond or two of the caller's time per picture.
+    if (lean) {
+        CU_TRY(cudaMemcpyAsync(c->d_pics[slot], hp, n * sizeof(PicDev), cudaMemcpyHostToDevice, c->s_main));
+    } else {
+        CU_TRY(cudaMemcpyAsync(c->d_pics[slot], hp, n * sizeof(PicDev), cudaMemcpyHostToDevice, c->s_pics));
+        CU_TRY(cudaEventRecord(c->pics_up[slot], c->s_pics));
+        CU_TRY(cudaStreamWaitEvent(c->s_main, c->pics_up[slot], 0));
+    }
     if (want_rgba) {
         // do not overwrite an RGBA ring slot that is still being read back
         CU_TRY(cudaStreamWaitEvent(c->s_main, c->rgba_read[rgba_ring], 0));
@@ -307,7 +313,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
     }
     CU_TRY(cudaEventRecord(c->pics_done[slot], c->s_main));
     if (want_rgba) {
-        CU_TRY(cudaEventRecord(c->rgba_written[rgba_ring], c->s_main));
+        if (!lean) CU_TRY(cudaEventRecord(c->rgba_written[rgba_ring], c->s_main));  // lean: the read-back follows on s_main
         c->rgba_parity++;
     }
     return 0;
@@ -602,19 +608,25 @@ int h263cu_step_run(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags) {
 }
 
 static int submit_common(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs, uint32_t n_mbs,
-                         const h263cu_event* events, uint32_t n_units, uint32_t out_flags, bool trusted = false) {
+                         const h263cu_event* events, uint32_t n_units, uint32_t out_flags, bool trusted = false, bool lean = false) {
     if (!c || !pics || (!mbs && n_mbs) || (!events && n_units)) return H263CU_ERR_BAD_ARGUMENT;
     cudaSetDevice(c->device);
     const int slot = c->ring_pos;
     h263cu_step* s = &c->ring[slot];
-    // the copy engine may not overwrite side info that a kernel is still reading
-    CU_TRY(cudaStreamWaitEvent(c->s_h2d, c->ring_run_done[slot], 0));
     if (n_mbs > s->mb_cap || (size_t)n_units + 8 > s->ev_cap) CU_TRY(cudaEventSynchronize(c->ring_run_done[slot]));
-    int e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_h2d, trusted);
-    if (e) return e;
-    CU_TRY(cudaEventRecord(c->ring_h2d_done[slot], c->s_h2d));
-    CU_TRY(cudaStreamWaitEvent(c->s_main, c->ring_h2d_done[slot], 0));
-    e = run_step(c, s, out_flags);
+    int e;
+    if (lean) {
+        // in-order on s_main: the kernels that read this ring slot two submits ago precede these copies on the stream
+        if ((e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_main, trusted))) return e;
+        CU_TRY(cudaEventRecord(c->ring_h2d_done[slot], c->s_main));
+    } else {
+        // the copy engine may not overwrite side info that a kernel is still reading
+        CU_TRY(cudaStreamWaitEvent(c->s_h2d, c->ring_run_done[slot], 0));
+        if ((e = upload_into(c, s, pics, n_pics, mbs, n_mbs, events, n_units, c->s_h2d, trusted))) return e;
+        CU_TRY(cudaEventRecord(c->ring_h2d_done[slot], c->s_h2d));
+        CU_TRY(cudaStreamWaitEvent(c->s_main, c->ring_h2d_done[slot], 0));
+    }
+    e = run_step(c, s, out_flags, lean);
     if (e) return e;
     c->ring_pos ^= 1;  // the ring slot is taken only by a step that runs
     CU_TRY(cudaEventRecord(c->ring_run_done[slot], c->s_main));
@@ -628,13 +640,14 @@ int h263cu_submit_step(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, c
 
 static int submit_readback(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs, uint32_t n_mbs,
                            const h263cu_event* events, uint32_t n_units, uint32_t out_flags, uint8_t* host_rgba,
-                           const uint64_t* rgba_offsets, bool trusted) {
+                           const uint64_t* rgba_offsets, bool trusted, bool lean = false) {
     if (!host_rgba) return H263CU_ERR_BAD_ARGUMENT;
     out_flags |= H263CU_OUT_RGBA;
-    int e = submit_common(c, pics, n_pics, mbs, n_mbs, events, n_units, out_flags, trusted);
+    int e = submit_common(c, pics, n_pics, mbs, n_mbs, events, n_units, out_flags, trusted, lean);
     if (e) return e;
     const int ring = (int)((c->rgba_parity - 1) & 1u);  // the slot run_step just wrote
-    CU_TRY(cudaStreamWaitEvent(c->s_d2h, c->rgba_written[ring], 0));
+    const cudaStream_t s_d2h = lean ? c->s_main : c->s_d2h;
+    if (!lean) CU_TRY(cudaStreamWaitEvent(c->s_d2h, c->rgba_written[ring], 0));
     uint64_t off = 0;
     uint32_t i = 0;
     while (i < n_pics) {
@@ -650,17 +663,17 @@ static int submit_readback(h263cu_ctx* c, const h263cu_pic* pics, uint32_t n_pic
                    (!rgba_offsets || rgba_offsets[j] == rgba_offsets[j - 1] + c->rgba_slot))
                 j++;
             CU_TRY(cudaMemcpyAsync(host_rgba + dst, c->rgba(p.stream, ring), (size_t)(j - i) * c->rgba_slot,
-                                   cudaMemcpyDeviceToHost, c->s_d2h));
+                                   cudaMemcpyDeviceToHost, s_d2h));
             off = dst + (uint64_t)(j - i) * c->rgba_slot;
             i = j;
         } else {
             CU_TRY(cudaMemcpy2DAsync(host_rgba + dst, tight, c->rgba(p.stream, ring), c->rgba_pitch, tight, p.height,
-                                     cudaMemcpyDeviceToHost, c->s_d2h));
+                                     cudaMemcpyDeviceToHost, s_d2h));
             off = dst + (uint64_t)tight * p.height;
             i++;
         }
     }
-    CU_TRY(cudaEventRecord(c->rgba_read[ring], c->s_d2h));
+    CU_TRY(cudaEventRecord(c->rgba_read[ring], s_d2h));
     return 0;
 }
 
@@ -717,8 +730,10 @@ static int decode_step_scattered(h263cu_ctx* c, h263cu_parser* const* parsers, c
     }
     if (n_decoded) *n_decoded = np;
     if (np == 0) return 0;
+    // one picture of at most a 4CIF's macroblocks: the single-stream case (H263State), latency bound on driver calls
+    const bool lean = np == 1 && nm <= 1584;
     if (!host_rgba) {
-        e = submit_common(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags, true);
+        e = submit_common(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags, true, lean);
     } else {
         try {
             c->rgba_offsets.resize(np);
@@ -728,7 +743,7 @@ static int decode_step_scattered(h263cu_ctx* c, h263cu_parser* const* parsers, c
         }
         for (uint32_t i = 0; i < n; i++)
             if (c->pic_of_input[i] >= 0) c->rgba_offsets[(size_t)c->pic_of_input[i]] = (uint64_t)(positions ? positions[i] : i) * rgba_stride;
-        e = submit_readback(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags, host_rgba, c->rgba_offsets.data(), true);
+        e = submit_readback(c, st.pics, np, st.mbs, nm, st.events, nu, out_flags, host_rgba, c->rgba_offsets.data(), true, lean);
     }
     // the device stage has the step (or refused it): only now do the parsers move on
     h263fe::parse_step_finish(parsers, n, e == 0);
@@ -762,6 +777,11 @@ int h263cu_stream_info(h263cu_ctx* c, uint32_t stream, uint32_t* width, uint32_t
     if (pquant) *pquant = st.pquant;
     if (temporal_reference) *temporal_reference = st.tr;
     return 0;
+}
+
+uint32_t h263cu_stream_dims(h263cu_ctx* c, uint32_t stream) {
+    if (!c || stream >= c->max_streams || !c->streams[stream].has_pic) return 0u;
+    return ((uint32_t)c->streams[stream].w << 16) | c->streams[stream].h;
 }
 
 int h263cu_read_yuv(h263cu_ctx* c, uint32_t stream, uint8_t* y, uint8_t* cb, uint8_t* cr) {

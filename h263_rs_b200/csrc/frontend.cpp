@@ -42,9 +42,10 @@ void VlcTable::build(const VlcCode* codes, int n) {
 namespace {
 struct Tables {
     VlcTable t[5];
-    // TCOEF again, laid out for the event loop: one word per 12-bit prefix =
-    //   len[4:0] | kind[6:5] | last[7] | (run << 10 | level)[31:16]   (level > 0: the sign bit follows the code)
-    // so that code, sign and the packed narrow event unit come from one load
+    // TCOEF again, laid out for the event loop: one word per (max code length + 1)-bit prefix, i.e. code AND sign bit =
+    //   bits consumed[4:0] (code + sign) | kind[6:5] | last[7] | (run << 10 | level as a signed 10-bit field)[31:16]
+    // so that one load yields the length to skip and the finished narrow event unit.  Escapes / invalid prefixes
+    // carry the code length alone.
     std::vector<uint32_t> tcoef_fast;
     int tcoef_bits = 0;
     Tables() {
@@ -53,12 +54,17 @@ struct Tables {
         t[T_CBPY].build(CBPY_CODES, CBPY_CODES_COUNT);
         t[T_MVD].build(MVD_CODES, MVD_CODES_COUNT);
         t[T_TCOEF].build(TCOEF_CODES, TCOEF_CODES_COUNT);
-        tcoef_bits = t[T_TCOEF].max_len;
-        tcoef_fast.resize(t[T_TCOEF].lut.size());
+        tcoef_bits = t[T_TCOEF].max_len + 1;
+        tcoef_fast.resize(t[T_TCOEF].lut.size() * 2);
         for (size_t i = 0; i < tcoef_fast.size(); i++) {
-            const VlcEntry& e = t[T_TCOEF].lut[i];
+            const VlcEntry& e = t[T_TCOEF].lut[i >> 1];
             uint32_t w = e.len() | (e.kind() << 5);
-            if (e.kind() == 0) w |= ((uint32_t)(e.a != 0) << 7) | ((((uint32_t)e.b << 10) | (uint32_t)e.c) << 16);
+            if (e.kind() == 0) {
+                // the sign bit is the bit right after the code: bit (max_len - len) of the index, counted from the LSB
+                const uint32_t sign = (uint32_t)(i >> (t[T_TCOEF].max_len - e.len())) & 1u;
+                const uint32_t level = sign ? (0u - (uint32_t)e.c) & 0x3FFu : (uint32_t)e.c;
+                w = (e.len() + 1u) | ((uint32_t)(e.a != 0) << 7) | ((((uint32_t)e.b << 10) | level) << 16);
+            }
             tcoef_fast[i] = w;
         }
     }
@@ -376,14 +382,11 @@ static H263_AI int parse_block_fast(BitReader& r, const uint32_t* __restrict tf,
         int last, run, level;
         uint32_t unit;
         if (__builtin_expect(kind == 0, 1)) {
-            if (__builtin_expect(len + 1 > r.avail(), 0)) return H263CU_ERR_UNHANDLED_IO_ERROR;  // code, then its sign bit
-            const uint32_t sign = (uint32_t)((w << len) >> 63);
-            r.consume(len + 1);
+            if (__builtin_expect(len > r.avail(), 0)) return H263CU_ERR_UNHANDLED_IO_ERROR;  // the code or its sign bit is cut off
+            r.consume(len);
             last = (int)((e >> 7) & 1u);
             unit = e >> 16;
-            run = (int)(unit >> 10);
-            // negate the 10-bit level field when the sign bit is set
-            unit = (unit & 0xFC00u) | ((((unit & 0x3FFu) ^ (0u - sign)) + sign) & 0x3FFu);
+            run = (int)(e >> 26);
         } else if (kind == 3) {
             if (len > r.avail()) return H263CU_ERR_UNHANDLED_IO_ERROR;
             r.consume(len);
@@ -404,9 +407,10 @@ static H263_AI int parse_block_fast(BitReader& r, const uint32_t* __restrict tf,
             return H263CU_ERR_INVALID_SHORT_COEFFICIENT;
         }
         idx += run;
-        ovf |= idx >= 64;
-        out[n] = (h263cu_event)unit;  // the caller leaves room for 64 units per block
-        n += ovf ? 0 : 1;
+        if (__builtin_expect(idx >= 64, 0))
+            ovf = true;
+        else if (!ovf)
+            out[n++] = (h263cu_event)unit;
         idx += 1;
         if (last) break;
     }

@@ -48,20 +48,21 @@ def reduce_sum(dist, value, device="cpu"):
     return float(t.item())
 
 
-def gather_to_rank0(dist, array, world, rank):
+def gather_to_rank0(dist, array, world, rank, device="cpu"):
     """Concatenates equally-shaped per-rank uint64 arrays on rank 0 in rank order (used to put
-    per-stream checksums of a sharded run back into global stream order for verification)."""
+    per-stream checksums / parity verdicts of a sharded run back into global order for verification).
+    `device` = where the collective's tensors must live ("cuda" with the nccl backend, "cpu" with gloo)."""
     array = np.ascontiguousarray(array, dtype=np.uint64)
     if dist is None:
         return [array]
     import torch
 
-    mine = torch.from_numpy(array.view(np.int64).copy())
-    parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-    dist.gather(mine, parts, dst=0)
+    mine = torch.from_numpy(array.view(np.int64).copy()).to(device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)  # every backend has all_gather; the volume is a few words
     if rank != 0:
         return None
-    return [p.numpy().view(np.uint64) for p in parts]
+    return [p.cpu().numpy().view(np.uint64) for p in parts]
 
 
 def interleave_shards(parts, n_streams):

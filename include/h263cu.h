@@ -276,6 +276,8 @@ int h263cu_group_sync(h263cu_group*);
  * chroma = ceil(w/2) x ceil(h/2).  Synchronise the context first. */
 int h263cu_stream_info(h263cu_ctx*, uint32_t stream, uint32_t* width, uint32_t* height, uint32_t* pic_type,
                        uint32_t* pquant, uint32_t* temporal_reference);
+/* width << 16 | height of the stream's last picture, 0 when it has none: the cheap form of h263cu_stream_info */
+uint32_t h263cu_stream_dims(h263cu_ctx*, uint32_t stream);
 int h263cu_read_yuv(h263cu_ctx*, uint32_t stream, uint8_t* y, uint8_t* cb, uint8_t* cr);
 /* RGBA of the stream's last picture (4*width*height bytes, R,G,B,A); requires that the
  * last step ran with H263CU_OUT_RGBA. */
