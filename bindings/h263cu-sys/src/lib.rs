@@ -111,6 +111,10 @@ pub struct h263cu_step {
     _private: [u8; 0],
 }
 #[repr(C)]
+pub struct h263cu_graph {
+    _private: [u8; 0],
+}
+#[repr(C)]
 pub struct h263cu_group {
     _private: [u8; 0],
 }
@@ -161,6 +165,9 @@ extern "C" {
     ) -> *mut h263cu_step;
     pub fn h263cu_step_free(c: *mut h263cu_ctx, s: *mut h263cu_step);
     pub fn h263cu_step_run(c: *mut h263cu_ctx, s: *mut h263cu_step, out_flags: u32) -> c_int;
+    pub fn h263cu_graph_build(c: *mut h263cu_ctx, steps: *const *mut h263cu_step, n_steps: u32, out_flags: u32, err: *mut c_int) -> *mut h263cu_graph;
+    pub fn h263cu_graph_launch(c: *mut h263cu_ctx, g: *mut h263cu_graph) -> c_int;
+    pub fn h263cu_graph_free(c: *mut h263cu_ctx, g: *mut h263cu_graph);
     pub fn h263cu_submit_step(
         c: *mut h263cu_ctx, pics: *const h263cu_pic, n_pics: u32, mbs: *const h263cu_mb, n_mbs: u32, events: *const h263cu_event,
         n_units: u32, out_flags: u32,
@@ -206,6 +213,7 @@ extern "C" {
     pub fn h263cu_timer_stop(c: *mut h263cu_ctx, milliseconds: *mut f32) -> c_int;
     pub fn h263cu_launch_count(c: *mut h263cu_ctx) -> u64;
     pub fn h263cu_tiled_launch_count(c: *mut h263cu_ctx) -> u64;
+    pub fn h263cu_host_times(c: *mut h263cu_ctx, parse_seconds: *mut f64, other_seconds: *mut f64, calls: *mut u64, reset: c_int) -> c_int;
     pub fn h263cu_profile_enable(c: *mut h263cu_ctx, enable: c_int) -> c_int;
     pub fn h263cu_profile_read(c: *mut h263cu_ctx, ms2: *mut f64, launches2: *mut u64) -> c_int;
 

@@ -59,11 +59,11 @@ SYMBOLS = [
     "h263cu_step_upload", "h263cu_step_free", "h263cu_step_run", "h263cu_submit_step",
     "h263cu_submit_step_readback", "h263cu_decode_step", "h263cu_sync", "h263cu_stream_info", "h263cu_read_yuv", "h263cu_read_rgba",
     "h263cu_checksums", "h263cu_timer_start", "h263cu_timer_stop", "h263cu_launch_count", "h263cu_tiled_launch_count",
-    "h263cu_profile_enable", "h263cu_profile_read",
+    "h263cu_profile_enable", "h263cu_profile_read", "h263cu_host_times",
     "h263cu_yuv420_to_rgba", "h263cu_deblock", "h263cu_quant_to_strength",
     "h263cu_flv_scan", "h263cu_flv_mux",
     "h263cu_test_read_bits", "h263cu_test_start_code", "h263cu_test_read_vlc", "h263cu_test_decode_block",
-    "h263cu_readback_wait", "h263cu_stream_dims", "h263cu_group_create", "h263cu_group_destroy", "h263cu_group_size", "h263cu_group_ctx",
+    "h263cu_readback_wait", "h263cu_stream_dims", "h263cu_graph_build", "h263cu_graph_launch", "h263cu_graph_free", "h263cu_group_create", "h263cu_group_destroy", "h263cu_group_size", "h263cu_group_ctx",
     "h263cu_group_decode_step", "h263cu_group_sync",
 ]
 
@@ -117,6 +117,11 @@ def lib():
         L.h263cu_decode_step.argtypes = [vp, vp, vp, vp, vp, u32, i32, u32, vp, u64, vp, C.POINTER(u32)]
         L.h263cu_sync.argtypes = [vp]
         L.h263cu_readback_wait.argtypes = [vp, u32]
+        L.h263cu_graph_build.restype = vp
+        L.h263cu_graph_build.argtypes = [vp, vp, u32, u32, C.POINTER(i32)]
+        L.h263cu_graph_launch.argtypes = [vp, vp]
+        L.h263cu_graph_free.argtypes = [vp, vp]
+        L.h263cu_graph_free.restype = None
         L.h263cu_stream_dims.restype = u32
         L.h263cu_stream_dims.argtypes = [vp, u32]
         L.h263cu_group_create.restype = vp
@@ -141,6 +146,7 @@ def lib():
         L.h263cu_tiled_launch_count.argtypes = [vp]
         L.h263cu_profile_enable.argtypes = [vp, i32]
         L.h263cu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.h263cu_host_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u64), i32]
         L.h263cu_yuv420_to_rgba.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, vp]
         L.h263cu_deblock.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_uint8, vp]
     L.h263cu_flv_scan.restype = C.c_int64

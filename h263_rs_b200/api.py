@@ -156,6 +156,21 @@ class Context:
     def step_free(self, step):
         self.L.h263cu_step_free(self.h, step)
 
+    def graph_build(self, steps, out_flags):
+        """n resident steps as one CUDA graph (h263cu_graph_build); the steps must outlive it."""
+        arr = (C.c_void_p * len(steps))(*steps)
+        err = C.c_int(0)
+        g = self.L.h263cu_graph_build(self.h, arr, len(steps), out_flags, C.byref(err))
+        if not g:
+            raise H263Error(err.value)
+        return g
+
+    def graph_launch(self, graph):
+        check(self.L.h263cu_graph_launch(self.h, graph))
+
+    def graph_free(self, graph):
+        self.L.h263cu_graph_free(self.h, graph)
+
     def sync(self):
         check(self.L.h263cu_sync(self.h))
 

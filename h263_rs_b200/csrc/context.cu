@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -127,6 +128,10 @@ struct h263cu_ctx {
     size_t jobs_cap = 0;
 
     int force_kernel = 0;  // H263CU_KERNEL=mb|tile overrides the per-step choice (A/B checks)
+    // host time spent inside h263cu_decode_step, split into the bitstream parse and everything else (staging, driver
+    // calls): the north-star asks for the host parse time beside the device time
+    double host_parse_s = 0.0, host_other_s = 0.0;
+    uint64_t host_calls = 0;
     // interior origin (pixel 0,0) of a plane; the padding lies at negative offsets
     uint8_t* plane(int p, uint32_t stream, int slot) const {
         const size_t idx = (size_t)stream * 2 + (size_t)slot;
@@ -188,6 +193,32 @@ void prof_end(h263cu_ctx* c, cudaEvent_t a, cudaEvent_t b, int kind) {
     c->prof_spans.push_back({a, b, kind});
 }
 
+// The device-side descriptor of one picture, given the state of its stream BEFORE the picture (run_step and the graph
+// builder, which walks a simulated copy of the state, share it).
+PicDev make_picdev(const h263cu_ctx* c, const h263cu_pic& p, const StreamState& st, bool want_rgba, int rgba_ring) {
+    const int ref_slot = st.cur_slot, new_slot = st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot;
+    PicDev d;
+    std::memset(&d, 0, sizeof(d));
+    for (int k = 0; k < 3; k++) {
+        d.cur[k] = c->plane(k, p.stream, new_slot);
+        d.ref[k] = st.has_pic ? c->plane(k, p.stream, ref_slot) : nullptr;
+    }
+    d.rgba = want_rgba ? c->rgba(p.stream, rgba_ring) : nullptr;
+    d.cur_y4 = (uint32_t)((d.cur[0] - c->y_pool) >> 2);
+    d.cur_c4 = (uint32_t)((d.cur[1] - c->c_pool) >> 2);
+    d.ref_y4 = st.has_pic ? (uint32_t)((d.ref[0] - c->y_pool) >> 2) : 0u;
+    d.ref_c4 = st.has_pic ? (uint32_t)((d.ref[1] - c->c_pool) >> 2) : 0u;
+    d.rgba_row0 = want_rgba ? (uint32_t)((size_t)(d.rgba - c->rgba_pool) / c->rgba_pitch) : 0u;
+    d.first_event = p.first_event;
+    d.rgba_pitch = c->rgba_pitch;
+    d.w = p.width, d.h = p.height;
+    d.cw = (uint16_t)((p.width + 1) / 2), d.ch = (uint16_t)((p.height + 1) / 2);
+    d.pitch_y = (uint16_t)c->pitch_y, d.pitch_c = (uint16_t)c->pitch_c;
+    d.strength = h263cu_quant_to_strength[p.pquant & 31];
+    d.flags = p.flags;
+    return d;
+}
+
 // Validates a step against the context and the per-stream state, builds the PicDev array,
 // enqueues the kernels on s_main and advances the per-stream reference bookkeeping
 // (state.rs:464-483: the picture just decoded becomes the reference of the next one).
@@ -236,27 +267,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags, bool lean = fals
     PicDev* hp = c->h_pics[slot];
     for (uint32_t i = 0; i < n; i++) {
         const h263cu_pic& p = s->pics[i];
-        const StreamState& st = c->streams[p.stream];
-        const int ref_slot = st.cur_slot, new_slot = st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot;
-        PicDev d;
-        std::memset(&d, 0, sizeof(d));
-        for (int k = 0; k < 3; k++) {
-            d.cur[k] = c->plane(k, p.stream, new_slot);
-            d.ref[k] = st.has_pic ? c->plane(k, p.stream, ref_slot) : nullptr;
-        }
-        d.rgba = want_rgba ? c->rgba(p.stream, rgba_ring) : nullptr;
-        d.cur_y4 = (uint32_t)((d.cur[0] - c->y_pool) >> 2);
-        d.cur_c4 = (uint32_t)((d.cur[1] - c->c_pool) >> 2);
-        d.ref_y4 = st.has_pic ? (uint32_t)((d.ref[0] - c->y_pool) >> 2) : 0u;
-        d.ref_c4 = st.has_pic ? (uint32_t)((d.ref[1] - c->c_pool) >> 2) : 0u;
-        d.rgba_row0 = want_rgba ? (uint32_t)((size_t)(d.rgba - c->rgba_pool) / c->rgba_pitch) : 0u;
-        d.first_event = p.first_event;
-        d.rgba_pitch = c->rgba_pitch;
-        d.w = p.width, d.h = p.height;
-        d.cw = (uint16_t)((p.width + 1) / 2), d.ch = (uint16_t)((p.height + 1) / 2);
-        d.pitch_y = (uint16_t)c->pitch_y, d.pitch_c = (uint16_t)c->pitch_c;
-        d.strength = h263cu_quant_to_strength[p.pquant & 31];
-        d.flags = p.flags;
+        const PicDev d = make_picdev(c, p, c->streams[p.stream], want_rgba, rgba_ring);
         hp[i] = d;
     }
     cudaEvent_t pa = nullptr, pb = nullptr, qa = nullptr, qb = nullptr;
@@ -691,6 +702,7 @@ static int decode_step_scattered(h263cu_ctx* c, h263cu_parser* const* parsers, c
     if (!c || !parsers || !packets || !lens) return H263CU_ERR_BAD_ARGUMENT;
     if (n_decoded) *n_decoded = 0;
     if (n == 0) return 0;
+    const auto t_enter = std::chrono::steady_clock::now();
     cudaSetDevice(c->device);
     // capacities: a picture holds at most mbw * mbh macroblocks of this context; every event costs at least
     // 3 bits of bitstream and takes at most 2 units
@@ -722,8 +734,18 @@ static int decode_step_scattered(h263cu_ctx* c, h263cu_parser* const* parsers, c
         return H263CU_ERR_OUT_OF_MEMORY;
     }
     uint32_t np = 0, nm = 0, nu = 0;
+    const auto t_parse0 = std::chrono::steady_clock::now();
     e = h263fe::parse_step_deferred(parsers, packets, lens, stream_ids, n, threads, st.pics, st.mbs, (uint32_t)st.mb_cap, st.events,
                                     (uint32_t)st.ev_cap, &np, &nm, &nu, per_pic_err, c->pic_of_input.data(), c->max_w, c->max_h);
+    const auto t_parse1 = std::chrono::steady_clock::now();
+    c->host_parse_s += std::chrono::duration<double>(t_parse1 - t_parse0).count();
+    c->host_other_s += std::chrono::duration<double>(t_parse0 - t_enter).count();
+    c->host_calls++;
+    struct Tail {  // whatever follows the parse on any return path counts as "other"
+        h263cu_ctx* c;
+        std::chrono::steady_clock::time_point t;
+        ~Tail() { c->host_other_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); }
+    } tail{c, t_parse1};
     if (e) {
         h263fe::parse_step_finish(parsers, n, false);
         return e;
@@ -874,6 +896,15 @@ int h263cu_timer_stop(h263cu_ctx* c, float* ms) {
 uint64_t h263cu_launch_count(h263cu_ctx* c) { return c ? c->launches : 0; }
 uint64_t h263cu_tiled_launch_count(h263cu_ctx* c) { return c ? c->tiled_launches : 0; }
 
+int h263cu_host_times(h263cu_ctx* c, double* parse_seconds, double* other_seconds, uint64_t* calls, int reset) {
+    if (!c) return H263CU_ERR_BAD_ARGUMENT;
+    if (parse_seconds) *parse_seconds = c->host_parse_s;
+    if (other_seconds) *other_seconds = c->host_other_s;
+    if (calls) *calls = c->host_calls;
+    if (reset) c->host_parse_s = c->host_other_s = 0.0, c->host_calls = 0;
+    return 0;
+}
+
 int h263cu_profile_enable(h263cu_ctx* c, int enable) {
     if (!c) return H263CU_ERR_BAD_ARGUMENT;
     c->profiling = enable != 0;
@@ -904,6 +935,178 @@ int h263cu_readback_wait(h263cu_ctx* c, uint32_t age) {
     const int ring = (int)((c->rgba_parity - 1u - age) & 1u);
     CU_TRY(cudaEventSynchronize(c->rgba_read[ring]));
     return 0;
+}
+
+// ---- resident steps as ONE CUDA graph ---------------------------------------------------------------------------
+// A single stream's pictures are dependent launches of ~10 us each: issuing them one by one is bound by the launch
+// path.  h263cu_graph_build captures the launches of n resident steps into one graph; the descriptors of all their
+// pictures are computed once from a simulated walk of the per-stream state and live in their own device array.
+struct h263cu_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    PicDev* d_pics = nullptr;
+    uint32_t out_flags = 0;
+    uint64_t launches = 0, tiled_launches = 0;
+    uint32_t rgba_steps = 0;
+    uint32_t rgba_parity0 = 0;  // parity of the RGBA ring the capture assumed
+    std::vector<uint32_t> streams;        // streams the graph touches
+    std::vector<StreamState> before, after;  // their state the capture assumed / leaves behind
+};
+
+h263cu_graph* h263cu_graph_build(h263cu_ctx* c, h263cu_step* const* steps, uint32_t n_steps, uint32_t out_flags, int* err) {
+    int dummy;
+    if (!err) err = &dummy;
+    *err = 0;
+    if (!c || !steps || n_steps == 0) {
+        *err = H263CU_ERR_BAD_ARGUMENT;
+        return nullptr;
+    }
+    cudaSetDevice(c->device);
+    const bool want_rgba = (out_flags & H263CU_OUT_RGBA) != 0;
+    const bool want_deblock = want_rgba && (out_flags & H263CU_OUT_DEBLOCK) != 0;
+    h263cu_graph* g = new (std::nothrow) h263cu_graph();
+    if (!g) {
+        *err = H263CU_ERR_OUT_OF_MEMORY;
+        return nullptr;
+    }
+    auto fail = [&](int code) {
+        *err = code;
+        h263cu_graph_free(c, g);
+        return (h263cu_graph*)nullptr;
+    };
+    g->out_flags = out_flags;
+    g->rgba_parity0 = c->rgba_parity & 1u;
+    // ---- walk the steps over a copy of the stream state: the checks of run_step, the descriptors, the end state ----
+    std::vector<StreamState> sim;
+    std::vector<PicDev> picdev;
+    struct StepPlan {
+        size_t first_pic;
+        uint32_t max_w, max_h;
+        bool tiled, aligned16, wide_mv;
+    };
+    std::vector<StepPlan> plan;
+    try {
+        sim = c->streams;
+        std::vector<uint8_t> touched(c->max_streams, 0);
+        uint32_t parity = c->rgba_parity;
+        for (uint32_t k = 0; k < n_steps; k++) {
+            const h263cu_step* s = steps[k];
+            if (!s || s->pics.empty()) return fail(H263CU_ERR_BAD_ARGUMENT);
+            StepPlan sp{picdev.size(), 0, 0, true, true, false};
+            const uint32_t stamp = ++c->stamp;
+            for (const h263cu_pic& p : s->pics) {
+                if (p.stream >= c->max_streams || p.width == 0 || p.height == 0 || p.width > c->max_w || p.height > c->max_h)
+                    return fail(H263CU_ERR_CAPACITY);
+                if ((uint32_t)p.mb_w * 16 < p.width || (uint32_t)p.mb_h * 16 < p.height || (uint32_t)p.mb_w > c->mbw ||
+                    (uint32_t)p.mb_h > c->mbh || (uint64_t)p.first_mb + p.n_mbs > s->n_mbs ||
+                    (uint64_t)p.first_event + p.n_event_units > s->n_units || p.n_mbs != (uint32_t)p.mb_w * p.mb_h)
+                    return fail(H263CU_ERR_BAD_ARGUMENT);
+                StreamState& st = sim[p.stream];
+                if (st.stamp == stamp) return fail(H263CU_ERR_BAD_ARGUMENT);
+                st.stamp = stamp;
+                if (p.flags & H263CU_PICFLAG_HAS_INTER) {
+                    if (!st.has_pic) return fail(H263CU_ERR_UNCODED_IFRAME_BLOCKS);
+                    if (st.w != p.width || st.h != p.height) return fail(H263CU_ERR_REFERENCE_WOULD_ABORT);
+                    if (!(p.flags & H263CU_PICFLAG_MV_IN_RANGE)) sp.wide_mv = true;
+                    if (!st.padded) sp.tiled = false;
+                }
+                if ((p.width | p.height) & 15) sp.aligned16 = false;
+                sp.max_w = std::max<uint32_t>(sp.max_w, p.width), sp.max_h = std::max<uint32_t>(sp.max_h, p.height);
+                if (!touched[p.stream]) touched[p.stream] = 1, g->streams.push_back(p.stream);
+            }
+            if (c->force_kernel == 1) sp.tiled = false;
+            const int ring = (int)(parity & 1u);
+            for (const h263cu_pic& p : s->pics) {
+                StreamState& st = sim[p.stream];
+                picdev.push_back(make_picdev(c, p, st, want_rgba, ring));
+                st.cur_slot = (uint8_t)(st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot);
+                st.has_pic = true;
+                st.w = p.width, st.h = p.height;
+                st.pic_type = p.pic_type, st.pquant = p.pquant, st.tr = p.temporal_reference;
+                st.rgba_slot = want_rgba ? (int8_t)ring : (int8_t)-1;
+                st.padded = sp.tiled;
+            }
+            if (want_rgba) parity++, g->rgba_steps++;
+            g->launches += want_deblock ? 2 : 1;
+            if (sp.tiled) g->tiled_launches++;
+            plan.push_back(sp);
+        }
+        for (uint32_t sid : g->streams) g->before.push_back(c->streams[sid]), g->after.push_back(sim[sid]);
+    } catch (const std::bad_alloc&) {
+        return fail(H263CU_ERR_OUT_OF_MEMORY);
+    }
+    if (cudaMalloc((void**)&g->d_pics, picdev.size() * sizeof(PicDev)) != cudaSuccess) return fail(H263CU_ERR_OUT_OF_MEMORY);
+    if (cudaMemcpy(g->d_pics, picdev.data(), picdev.size() * sizeof(PicDev), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(H263CU_ERR_CUDA);
+    // ---- capture ----
+    if (cudaStreamSynchronize(c->s_main) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    if (cudaStreamBeginCapture(c->s_main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail(H263CU_ERR_CUDA);
+    const Pools pools{c->y_pool, c->c_pool, c->rgba_pool, c->pitch_y, c->pitch_c, c->rgba_pitch};
+    for (uint32_t k = 0; k < n_steps; k++) {
+        const h263cu_step* s = steps[k];
+        const StepPlan& sp = plan[k];
+        const PicDev* dp = g->d_pics + sp.first_pic;
+        launch_recon(dp, s->d_mbs, s->d_events, s->n_mbs, want_rgba && !want_deblock, sp.tiled ? (sp.aligned16 ? 1 : 2) : 0, sp.wide_mv, pools,
+                     &c->rgba_map, c->s_main);
+        if (want_deblock) {
+            if (sp.aligned16 && c->force_kernel != 1)
+                launch_deblock_rgba_tile(dp, (uint32_t)s->pics.size(), sp.max_w, sp.max_h, c->s_main);
+            else
+                launch_deblock_rgba(dp, (uint32_t)s->pics.size(), sp.max_w, sp.max_h, c->s_main);
+        }
+    }
+    if (cudaStreamEndCapture(c->s_main, &g->graph) != cudaSuccess || !g->graph) {
+        cudaGetLastError();
+        return fail(H263CU_ERR_CUDA);
+    }
+    if (cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(H263CU_ERR_CUDA);
+    }
+    return g;
+}
+
+int h263cu_graph_launch(h263cu_ctx* c, h263cu_graph* g) {
+    if (!c || !g || !g->exec) return H263CU_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    // the graph holds plane addresses: it runs only from the state it was captured for
+    if (g->rgba_steps && (c->rgba_parity & 1u) != g->rgba_parity0) return H263CU_ERR_BAD_ARGUMENT;
+    for (size_t i = 0; i < g->streams.size(); i++) {
+        const StreamState &a = c->streams[g->streams[i]], &b = g->before[i];
+        if (a.has_pic != b.has_pic || (a.has_pic && (a.cur_slot != b.cur_slot || a.w != b.w || a.h != b.h || a.padded != b.padded)))
+            return H263CU_ERR_BAD_ARGUMENT;
+    }
+    if (g->rgba_steps) {  // read-backs of earlier steps may still hold the RGBA ring
+        CU_TRY(cudaStreamWaitEvent(c->s_main, c->rgba_read[0], 0));
+        CU_TRY(cudaStreamWaitEvent(c->s_main, c->rgba_read[1], 0));
+    }
+    CU_TRY(cudaGraphLaunch(g->exec, c->s_main));
+    for (size_t i = 0; i < g->streams.size(); i++) {
+        StreamState& st = c->streams[g->streams[i]];
+        const uint32_t seen = st.seen, stamp = st.stamp;
+        st = g->after[i];
+        st.seen = seen, st.stamp = stamp;
+    }
+    c->rgba_parity += g->rgba_steps;
+    c->launches += g->launches;
+    c->tiled_launches += g->tiled_launches;
+    if (g->rgba_steps) {
+        CU_TRY(cudaEventRecord(c->rgba_written[0], c->s_main));
+        CU_TRY(cudaEventRecord(c->rgba_written[1], c->s_main));
+    }
+    return 0;
+}
+
+void h263cu_graph_free(h263cu_ctx* c, h263cu_graph* g) {
+    if (!g) return;
+    if (c) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->s_main);
+    }
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    if (g->d_pics) cudaFree(g->d_pics);
+    delete g;
 }
 
 // ---- one process, several GPUs: a group of contexts fed by ONE shared pool of parser threads ----

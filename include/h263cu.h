@@ -223,6 +223,16 @@ void h263cu_step_free(h263cu_ctx*, h263cu_step*);
  * requested outputs.  Each stream's "last picture" becomes the reference of its next one
  * (state.rs:72-78). */
 int h263cu_step_run(h263cu_ctx*, h263cu_step*, uint32_t out_flags);
+/* n resident steps as ONE CUDA graph.  A single stream's pictures are dependent launches of about ten microseconds
+ * each (BASELINE.json configs[1]); captured into a graph they cost one launch call together.  The graph holds plane
+ * addresses, so it is bound to the per-stream state it was built from: h263cu_graph_launch checks that every stream
+ * the steps touch is where the capture assumed (plane slot, size, picture present), launches, and advances the
+ * bookkeeping as the steps would have.  A graph over an even number of pictures per stream leaves the slots where they
+ * started and can be launched again at once.  The steps must outlive the graph. */
+typedef struct h263cu_graph h263cu_graph;
+h263cu_graph* h263cu_graph_build(h263cu_ctx*, h263cu_step* const* steps, uint32_t n_steps, uint32_t out_flags, int* err);
+int h263cu_graph_launch(h263cu_ctx*, h263cu_graph*);
+void h263cu_graph_free(h263cu_ctx*, h263cu_graph*);
 /* upload + run through an internal double-buffered ring (the streaming form) */
 int h263cu_submit_step(h263cu_ctx*, const h263cu_pic* pics, uint32_t n_pics, const h263cu_mb* mbs,
                        uint32_t n_mbs, const h263cu_event* events, uint32_t n_units, uint32_t out_flags);
@@ -296,6 +306,9 @@ uint64_t h263cu_launch_count(h263cu_ctx*);
 /* How many of the reconstruction launches took the tiled kernel (the fast path: references with a
  * replicated border; any picture size) rather than the generic warp-per-macroblock kernel. */
 uint64_t h263cu_tiled_launch_count(h263cu_ctx*);
+/* Host time spent inside h263cu_decode_step since the last reset: the bitstream parse, and everything else (staging,
+ * driver calls).  Reported beside the device time (the parse is the host's share of decode_next_picture). */
+int h263cu_host_times(h263cu_ctx*, double* parse_seconds, double* other_seconds, uint64_t* calls, int reset);
 /* Per-kernel timing: when enabled, every recon / deblock launch is bracketed by CUDA events
  * on the launching stream.  h263cu_profile_read synchronises, accumulates the elapsed times
  * since the last read into ms[0] (recon) / ms[1] (deblock+rgba) and the launch counts into

@@ -563,3 +563,45 @@ def test_device_group_shares_parser_threads_across_contexts():
     for h in host:
         L.h263cu_free_pinned(h)
     grp.close()
+
+
+def test_resident_steps_as_one_cuda_graph():
+    """h263cu_graph_*: the resident steps of one stream captured into ONE CUDA graph (BASELINE.json configs[1]: a
+    single stream is a chain of dependent launches).  The graph is bound to the stream state it was built from: it
+    runs from there, leaves the bookkeeping where the steps would have, can be launched again when the picture count
+    is even, and refuses to run from any other state.  Planes and RGBA match the oracle."""
+    pk = synth.make_stream(352, 288, 7, 91, mv_mode=1)
+    ref = oracle_decode_stream(pk)
+    ctx = api.Context(0, 1, 352, 288)
+    ps = frontend.Parser(1)
+    steps = []
+    for p in pk:
+        pic, mbs, ev = ps.parse_picture(p)
+        steps.append(ctx.step_upload(pic, mbs, ev))
+    ctx.step_run(steps[0], _lib.OUT_RGBA)          # the I picture, the ordinary way
+    g = ctx.graph_build(steps[1:7], _lib.OUT_RGBA)  # six P pictures: an even count
+    n0 = ctx.launch_count()
+    ctx.graph_launch(g)
+    ctx.sync()
+    assert ctx.launch_count() == n0 + 6 and ctx.tiled_launch_count() == 7
+    y, cb, cr = ctx.read_yuv(0)
+    assert np.array_equal(y, ref[6]["y"]) and np.array_equal(cb, ref[6]["cb"]) and np.array_equal(cr, ref[6]["cr"])
+    assert np.array_equal(ctx.read_rgba(0), ref[6]["rgba"])
+    assert ctx.stream_info(0)["tr"] == ref[6]["info"]["tr"]
+    # an even number of pictures leaves the plane slots where they started: the same graph runs again (P on top of P:
+    # the result differs from the stream's, the call must simply be accepted), an odd-length one would not fit after it
+    ctx.graph_launch(g)
+    ctx.sync()
+    g_odd = ctx.graph_build(steps[1:4], _lib.OUT_RGBA)
+    ctx.graph_launch(g_odd)
+    with pytest.raises(_lib.H263Error) as e:  # the slots have moved on by three pictures: not the captured state
+        ctx.graph_launch(g_odd)
+    assert e.value.code == _lib.ERR_BAD_ARGUMENT
+    with pytest.raises(_lib.H263Error):
+        ctx.graph_launch(g)
+    ctx.sync()
+    ctx.graph_free(g)
+    ctx.graph_free(g_odd)
+    for s in steps:
+        ctx.step_free(s)
+    ctx.close()
