@@ -236,9 +236,17 @@ impl H263State {
     pub fn new(decoder_options: DecoderOption) -> Self {
         Self::with_device(decoder_options, 0)
     }
+    /// EXTENSION beyond the reference: a state that decodes Sorenson disposable P pictures (shown, never predicted
+    /// from) instead of failing them with `UnimplementedDecoding` like the reference (`macroblock.rs:461-465`).
+    pub fn with_disposable_pictures(decoder_options: DecoderOption) -> Self {
+        Self::with_bits(decoder_options, decoder_options.bits() as u32 | sys::H263CU_OPT_DECODE_DISPOSABLE, 0)
+    }
     /// Like `new`, on a chosen CUDA device.
     pub fn with_device(decoder_options: DecoderOption, device: i32) -> Self {
-        let parser = unsafe { sys::h263cu_parser_create(decoder_options.bits() as u32) };
+        Self::with_bits(decoder_options, decoder_options.bits() as u32, device)
+    }
+    fn with_bits(decoder_options: DecoderOption, bits: u32, device: i32) -> Self {
+        let parser = unsafe { sys::h263cu_parser_create(bits) };
         assert!(!parser.is_null(), "out of memory");
         Self { decoder_options, device, parser, ctx: std::ptr::null_mut(), ctx_w: 0, ctx_h: 0, last: None }
     }
@@ -271,7 +279,7 @@ impl H263State {
 
     /// Decode the next picture in the bitstream (`state.rs:138-489`).
     pub fn decode_next_picture<R: Read>(&mut self, reader: &mut H263Reader<R>) -> Result<()> {
-        let options = self.decoder_options.bits() as u32;
+        let options = unsafe { sys::h263cu_parser_options(self.parser) };
         let packet = reader.packet()?;
         let mut pic = sys::h263cu_pic::default();
         let rc = unsafe { sys::h263cu_peek_picture(options, packet.as_ptr(), packet.len(), &mut pic) };

@@ -33,6 +33,8 @@ pub const H263CU_ERR_OUT_OF_MEMORY: c_int = -106;
 /// DecoderOption bits (h263/src/decoder/types.rs:3-18)
 pub const H263CU_OPT_SORENSON_SPARK_BITSTREAM: u32 = 1;
 pub const H263CU_OPT_USE_SCALABILITY_MODE: u32 = 2;
+/// EXTENSION beyond the reference: decode Sorenson disposable P pictures (macroblock.rs:461-465 fails them)
+pub const H263CU_OPT_DECODE_DISPOSABLE: u32 = 0x100;
 
 pub const H263CU_PIC_I: u8 = 0;
 pub const H263CU_PIC_P: u8 = 1;
@@ -41,6 +43,7 @@ pub const H263CU_PIC_OTHER: u8 = 3;
 pub const H263CU_PICFLAG_DEBLOCK: u8 = 1;
 pub const H263CU_PICFLAG_HAS_INTER: u8 = 2;
 pub const H263CU_PICFLAG_MV_IN_RANGE: u8 = 4;
+pub const H263CU_PICFLAG_DISPOSABLE: u8 = 8;
 pub const H263CU_MB_INTER: u8 = 1;
 pub const H263CU_MB_WIDE: u8 = 2;
 pub const H263CU_MB_FOURMV: u8 = 4;

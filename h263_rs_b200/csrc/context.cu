@@ -60,8 +60,33 @@ struct StreamState {
     uint16_t tr = 0;
     uint32_t stamp = 0;
     uint32_t seen = 0;    // epoch of the last h263cu_decode_step that named this stream (duplicate check)
-    bool padded = false;  // the last picture's planes carry the replicated border (tiled kernel)
+    // the prediction source of the next picture: the last NON-disposable picture.  Identical to the last picture unless
+    // the stream carries disposable P pictures (H263CU_PICFLAG_DISPOSABLE), which are shown but never predicted from.
+    bool has_ref = false;
+    uint8_t ref_slot = 0;
+    uint16_t ref_w = 0, ref_h = 0;
+    bool padded = false;  // the reference picture's planes carry the replicated border (tiled kernel)
 };
+
+// where the next picture of a stream is reconstructed: never over its prediction source
+inline int next_slot(const StreamState& st) { return st.has_ref ? (st.ref_slot ^ 1) : (st.has_pic ? (st.cur_slot ^ 1) : 0); }
+
+// state.rs:464-483 on the device side: the picture becomes the stream's last picture and, unless it is disposable,
+// the reference of the next one
+inline void advance_stream(StreamState& st, const h263cu_pic& p, bool want_rgba, int rgba_ring, bool tiled) {
+    const int slot = next_slot(st);
+    st.cur_slot = (uint8_t)slot;
+    st.has_pic = true;
+    st.w = p.width, st.h = p.height;
+    st.pic_type = p.pic_type, st.pquant = p.pquant, st.tr = p.temporal_reference;
+    st.rgba_slot = want_rgba ? (int8_t)rgba_ring : (int8_t)-1;
+    if (!(p.flags & H263CU_PICFLAG_DISPOSABLE)) {
+        st.has_ref = true;
+        st.ref_slot = (uint8_t)slot;
+        st.ref_w = p.width, st.ref_h = p.height;
+        st.padded = tiled;
+    }
+}
 
 }  // namespace
 
@@ -196,18 +221,18 @@ void prof_end(h263cu_ctx* c, cudaEvent_t a, cudaEvent_t b, int kind) {
 // The device-side descriptor of one picture, given the state of its stream BEFORE the picture (run_step and the graph
 // builder, which walks a simulated copy of the state, share it).
 PicDev make_picdev(const h263cu_ctx* c, const h263cu_pic& p, const StreamState& st, bool want_rgba, int rgba_ring) {
-    const int ref_slot = st.cur_slot, new_slot = st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot;
+    const int ref_slot = st.ref_slot, new_slot = next_slot(st);
     PicDev d;
     std::memset(&d, 0, sizeof(d));
     for (int k = 0; k < 3; k++) {
         d.cur[k] = c->plane(k, p.stream, new_slot);
-        d.ref[k] = st.has_pic ? c->plane(k, p.stream, ref_slot) : nullptr;
+        d.ref[k] = st.has_ref ? c->plane(k, p.stream, ref_slot) : nullptr;
     }
     d.rgba = want_rgba ? c->rgba(p.stream, rgba_ring) : nullptr;
     d.cur_y4 = (uint32_t)((d.cur[0] - c->y_pool) >> 2);
     d.cur_c4 = (uint32_t)((d.cur[1] - c->c_pool) >> 2);
-    d.ref_y4 = st.has_pic ? (uint32_t)((d.ref[0] - c->y_pool) >> 2) : 0u;
-    d.ref_c4 = st.has_pic ? (uint32_t)((d.ref[1] - c->c_pool) >> 2) : 0u;
+    d.ref_y4 = st.has_ref ? (uint32_t)((d.ref[0] - c->y_pool) >> 2) : 0u;
+    d.ref_c4 = st.has_ref ? (uint32_t)((d.ref[1] - c->c_pool) >> 2) : 0u;
     d.rgba_row0 = want_rgba ? (uint32_t)((size_t)(d.rgba - c->rgba_pool) / c->rgba_pitch) : 0u;
     d.first_event = p.first_event;
     d.rgba_pitch = c->rgba_pitch;
@@ -247,8 +272,8 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags, bool lean = fals
         if (st.stamp == stamp) return H263CU_ERR_BAD_ARGUMENT;  // a stream appears once per step
         st.stamp = stamp;
         if (p.flags & H263CU_PICFLAG_HAS_INTER) {
-            if (!st.has_pic) return H263CU_ERR_UNCODED_IFRAME_BLOCKS;             // gather.rs:149
-            if (st.w != p.width || st.h != p.height) return H263CU_ERR_REFERENCE_WOULD_ABORT;
+            if (!st.has_ref) return H263CU_ERR_UNCODED_IFRAME_BLOCKS;             // gather.rs:149
+            if (st.ref_w != p.width || st.ref_h != p.height) return H263CU_ERR_REFERENCE_WOULD_ABORT;
         }
         max_w = std::max<uint32_t>(max_w, p.width);
         max_h = std::max<uint32_t>(max_h, p.height);
@@ -312,16 +337,7 @@ int run_step(h263cu_ctx* c, h263cu_step* s, uint32_t out_flags, bool lean = fals
     c->pic_ring_pos = (c->pic_ring_pos + 1) % h263cu_ctx::PIC_RING;
     c->launches += want_deblock ? 2 : 1;
     if (tiled) c->tiled_launches++;
-    for (uint32_t i = 0; i < n; i++) {
-        const h263cu_pic& p = s->pics[i];
-        StreamState& st = c->streams[p.stream];
-        st.cur_slot = (uint8_t)(st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot);
-        st.has_pic = true;
-        st.w = p.width, st.h = p.height;
-        st.pic_type = p.pic_type, st.pquant = p.pquant, st.tr = p.temporal_reference;
-        st.rgba_slot = want_rgba ? (int8_t)rgba_ring : (int8_t)-1;
-        st.padded = tiled;
-    }
+    for (uint32_t i = 0; i < n; i++) advance_stream(c->streams[s->pics[i].stream], s->pics[i], want_rgba, rgba_ring, tiled);
     CU_TRY(cudaEventRecord(c->pics_done[slot], c->s_main));
     if (want_rgba) {
         if (!lean) CU_TRY(cudaEventRecord(c->rgba_written[rgba_ring], c->s_main));  // lean: the read-back follows on s_main
@@ -1005,8 +1021,8 @@ h263cu_graph* h263cu_graph_build(h263cu_ctx* c, h263cu_step* const* steps, uint3
                 if (st.stamp == stamp) return fail(H263CU_ERR_BAD_ARGUMENT);
                 st.stamp = stamp;
                 if (p.flags & H263CU_PICFLAG_HAS_INTER) {
-                    if (!st.has_pic) return fail(H263CU_ERR_UNCODED_IFRAME_BLOCKS);
-                    if (st.w != p.width || st.h != p.height) return fail(H263CU_ERR_REFERENCE_WOULD_ABORT);
+                    if (!st.has_ref) return fail(H263CU_ERR_UNCODED_IFRAME_BLOCKS);
+                    if (st.ref_w != p.width || st.ref_h != p.height) return fail(H263CU_ERR_REFERENCE_WOULD_ABORT);
                     if (!(p.flags & H263CU_PICFLAG_MV_IN_RANGE)) sp.wide_mv = true;
                     if (!st.padded) sp.tiled = false;
                 }
@@ -1019,12 +1035,7 @@ h263cu_graph* h263cu_graph_build(h263cu_ctx* c, h263cu_step* const* steps, uint3
             for (const h263cu_pic& p : s->pics) {
                 StreamState& st = sim[p.stream];
                 picdev.push_back(make_picdev(c, p, st, want_rgba, ring));
-                st.cur_slot = (uint8_t)(st.has_pic ? (st.cur_slot ^ 1) : st.cur_slot);
-                st.has_pic = true;
-                st.w = p.width, st.h = p.height;
-                st.pic_type = p.pic_type, st.pquant = p.pquant, st.tr = p.temporal_reference;
-                st.rgba_slot = want_rgba ? (int8_t)ring : (int8_t)-1;
-                st.padded = sp.tiled;
+                advance_stream(st, p, want_rgba, ring, sp.tiled);
             }
             if (want_rgba) parity++, g->rgba_steps++;
             g->launches += want_deblock ? 2 : 1;
@@ -1073,7 +1084,8 @@ int h263cu_graph_launch(h263cu_ctx* c, h263cu_graph* g) {
     if (g->rgba_steps && (c->rgba_parity & 1u) != g->rgba_parity0) return H263CU_ERR_BAD_ARGUMENT;
     for (size_t i = 0; i < g->streams.size(); i++) {
         const StreamState &a = c->streams[g->streams[i]], &b = g->before[i];
-        if (a.has_pic != b.has_pic || (a.has_pic && (a.cur_slot != b.cur_slot || a.w != b.w || a.h != b.h || a.padded != b.padded)))
+        if (a.has_pic != b.has_pic || (a.has_pic && a.cur_slot != b.cur_slot) || a.has_ref != b.has_ref ||
+            (a.has_ref && (a.ref_slot != b.ref_slot || a.ref_w != b.ref_w || a.ref_h != b.ref_h || a.padded != b.padded)))
             return H263CU_ERR_BAD_ARGUMENT;
     }
     if (g->rgba_steps) {  // read-backs of earlier steps may still hold the RGBA ring

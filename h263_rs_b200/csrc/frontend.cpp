@@ -267,6 +267,7 @@ struct h263cu_parser {
     bool has_reference = false;
     int last_fmt_kind = -1;
     uint16_t last_w = 0, last_h = 0;
+    uint16_t ref_w = 0, ref_h = 0;  // size of the last non-disposable picture (H263CU_OPT_DECODE_DISPOSABLE)
     // scratch
     std::vector<Mv> mvs;  // 4 per MB, current picture
     // per-picture staging used by h263cu_parse_step
@@ -280,7 +281,7 @@ struct h263cu_parser {
         bool valid = false;
         bool has_last = false, has_reference = false;
         int fmt_kind = -1;
-        uint16_t w = 0, h = 0;
+        uint16_t w = 0, h = 0, ref_w = 0, ref_h = 0;
     } pending;
 };
 
@@ -289,7 +290,7 @@ namespace {
 struct PendingState {
     bool has_last, has_reference;
     int fmt_kind;
-    uint16_t w, h;
+    uint16_t w, h, ref_w, ref_h;
 };
 
 // One block (block.rs:670-755).  Events go to ev_run/ev_level; returns 0 or an error.
@@ -443,6 +444,8 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
     if (capacity > mb_cap) return H263CU_ERR_CAPACITY;
 
     const bool is_sorenson = (p->options & H263CU_OPT_SORENSON_SPARK_BITSTREAM) != 0;
+    // EXTENSION: disposable P pictures parse like P pictures and never become the reference
+    const bool decode_disposable = (p->options & H263CU_OPT_DECODE_DISPOSABLE) != 0;
     const bool is_i = hd.pic_type == H263CU_PIC_I;
     const VlcTable& TMt = vlc_table(is_i ? T_MCBPC_I : T_MCBPC_P);
     const VlcTable& TCt = vlc_table(T_CBPY);
@@ -486,8 +489,8 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
                     break;
                 }
             }
-            if (!is_i && hd.pic_type != H263CU_PIC_P) {  // disposable / unsupported types
-                err = H263CU_ERR_UNIMPLEMENTED_DECODING;
+            if (!is_i && hd.pic_type != H263CU_PIC_P && !(decode_disposable && hd.pic_type == H263CU_PIC_DISPOSABLE_P)) {
+                err = H263CU_ERR_UNIMPLEMENTED_DECODING;  // disposable (without the extension) / unsupported types
                 break;
             }
             if (!hd.type_supported) {
@@ -716,7 +719,10 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
     // gather()'s checks (gather.rs:148-149; SURVEY.md 7.0 on mismatching dimensions)
     if (any_inter) {
         if (!(p->has_reference && p->has_last)) return H263CU_ERR_UNCODED_IFRAME_BLOCKS;
-        if (p->last_w != W || p->last_h != H) return H263CU_ERR_REFERENCE_WOULD_ABORT;
+        // the prediction source: the last picture (the reference's get_reference_picture, state.rs:72-78), or the last
+        // non-disposable one under the extension
+        const uint16_t rw = decode_disposable ? p->ref_w : p->last_w, rh = decode_disposable ? p->ref_h : p->last_h;
+        if (rw != W || rh != H) return H263CU_ERR_REFERENCE_WOULD_ABORT;
     }
 
     std::memset(pic, 0, sizeof(*pic));
@@ -725,8 +731,9 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
     pic->mb_w = (uint8_t)mb_w, pic->mb_h = (uint8_t)mb_h;
     pic->pic_type = hd.pic_type;
     pic->pquant = hd.quant;
+    const bool disposable = decode_disposable && hd.pic_type == H263CU_PIC_DISPOSABLE_P;
     pic->flags = (uint8_t)((hd.deblock ? H263CU_PICFLAG_DEBLOCK : 0) | (any_inter ? H263CU_PICFLAG_HAS_INTER : 0) |
-                           (mv_in_range ? H263CU_PICFLAG_MV_IN_RANGE : 0));
+                           (mv_in_range ? H263CU_PICFLAG_MV_IN_RANGE : 0) | (disposable ? H263CU_PICFLAG_DISPOSABLE : 0));
     pic->version = hd.version < 0 ? 0xFF : (uint8_t)hd.version;
     pic->first_mb = mb_base;
     pic->n_mbs = capacity;
@@ -741,6 +748,7 @@ static int parse_picture_impl(h263cu_parser* p, const uint8_t* data, size_t len,
     if (hd.pic_type != H263CU_PIC_DISPOSABLE_P) pending->has_reference = true;
     pending->fmt_kind = hd.fmt_kind;
     pending->w = (uint16_t)W, pending->h = (uint16_t)H;
+    pending->ref_w = disposable ? p->ref_w : (uint16_t)W, pending->ref_h = disposable ? p->ref_h : (uint16_t)H;
     return 0;
 }
 
@@ -749,6 +757,7 @@ static inline void commit(h263cu_parser* p, const PendingState& s) {
     p->has_reference = s.has_reference;
     p->last_fmt_kind = s.fmt_kind;
     p->last_w = s.w, p->last_h = s.h;
+    p->ref_w = s.ref_w, p->ref_h = s.ref_h;
 }
 
 }  // namespace
@@ -836,6 +845,7 @@ void h263cu_parser_reset(h263cu_parser* p) {
     p->has_last = p->has_reference = false;
     p->last_fmt_kind = -1;
     p->last_w = p->last_h = 0;
+    p->ref_w = p->ref_h = 0;
 }
 
 int h263cu_peek_picture(uint32_t decoder_options, const uint8_t* data, size_t len, h263cu_pic* pic) {
@@ -963,6 +973,7 @@ static int parse_step_impl(h263cu_parser* const* parsers, const uint8_t* const* 
                 p->pending.valid = true;
                 p->pending.has_last = pend[i].has_last, p->pending.has_reference = pend[i].has_reference;
                 p->pending.fmt_kind = pend[i].fmt_kind, p->pending.w = pend[i].w, p->pending.h = pend[i].h;
+                p->pending.ref_w = pend[i].ref_w, p->pending.ref_h = pend[i].ref_h;
             }
         }
     };
@@ -1112,6 +1123,7 @@ void parse_step_finish(h263cu_parser* const* parsers, uint32_t n, bool accept) {
         if (accept) {
             p->has_last = p->pending.has_last, p->has_reference = p->pending.has_reference;
             p->last_fmt_kind = p->pending.fmt_kind, p->last_w = p->pending.w, p->last_h = p->pending.h;
+            p->ref_w = p->pending.ref_w, p->ref_h = p->pending.ref_h;
         }
         p->pending.valid = false;
     }

@@ -121,7 +121,7 @@ struct Gen {
         mb_h = (p.height + 15) / 16;
     }
 
-    void header(BitWriter& w, uint32_t tr, bool intra, uint32_t quant) {
+    void header(BitWriter& w, uint32_t tr, bool intra, uint32_t quant, bool disposable = false) {
         w.put(1, 17);  // PSC: sixteen zeros and a one
         if (P.flavour == 0) {
             w.put(P.version & 31, 5);
@@ -146,7 +146,7 @@ struct Gen {
                 w.put(W, 16);
                 w.put(H, 16);
             }
-            w.put(intra ? 0 : 1, 2);
+            w.put(intra ? 0 : (disposable ? 2 : 1), 2);  // Sorenson picture type: 0 I, 1 P, 2 disposable P (picture.rs:319-325)
             w.put(P.deblock_flag ? 1 : 0, 1);
             w.put(quant, 5);
             w.put(0, 1);  // PEI
@@ -261,7 +261,9 @@ struct Gen {
         const EncTables& E = enc();
         uint32_t qlo = std::max(1u, std::min(31u, P.qp_min)), qhi = std::max(qlo, std::min(31u, P.qp_max));
         int quant = rng.range((int)qlo, (int)qhi);
-        header(w, index, intra_pic, (uint32_t)quant);
+        // drawn only when asked for, so that streams without disposable pictures stay what they were
+        const bool disposable = !intra_pic && P.flavour == 0 && P.pct_disposable && rng.pct(P.pct_disposable);
+        header(w, index, intra_pic, (uint32_t)quant, disposable);
         const uint32_t n_mb = mb_w * mb_h;
         mvs.assign((size_t)n_mb * 4, Mv{0, 0});
         uint32_t stop_at = n_mb;

@@ -19,7 +19,7 @@ class SynthParams(C.Structure):
         ("pct_fourmv", C.c_uint32), ("pct_dquant", C.c_uint32), ("pct_cbp_inter", C.c_uint32),
         ("pct_cbp_intra", C.c_uint32), ("mean_events_x10", C.c_uint32), ("pct_escape", C.c_uint32),
         ("permille_overflow", C.c_uint32), ("mv_mode", C.c_uint32), ("truncate_permille", C.c_uint32),
-        ("reserved", C.c_uint32 * 4),
+        ("pct_disposable", C.c_uint32), ("reserved", C.c_uint32 * 3),
     ]
 
 

@@ -75,6 +75,10 @@ int h263cu_version(void);
 /* DecoderOption (h263/src/decoder/types.rs:3-18) */
 #define H263CU_OPT_SORENSON_SPARK_BITSTREAM 1u
 #define H263CU_OPT_USE_SCALABILITY_MODE 2u
+/* EXTENSION, beyond the reference: decode Sorenson disposable P pictures (picture type 2, FLV frame type 3) like P
+ * pictures that are shown but never become a reference.  The reference fails them with UnimplementedDecoding
+ * (macroblock.rs:461-465), and so does this library unless the bit is set at h263cu_parser_create. */
+#define H263CU_OPT_DECODE_DISPOSABLE 0x100u
 
 /* ---- side-info format (host -> device) ------------------------------------------------
  * One time step = one picture for each of n streams.  All three arrays live in
@@ -93,6 +97,9 @@ int h263cu_version(void);
  * device runs the reconstruction kernel without the clamped per-sample prediction path.  A producer that sets the
  * flag on a picture with longer vectors gets them clamped to the range. */
 #define H263CU_PICFLAG_MV_IN_RANGE 4u
+/* The picture is a disposable P picture decoded under H263CU_OPT_DECODE_DISPOSABLE: it becomes the stream's last
+ * picture but not the reference of the next one (the previous reference stays in place). */
+#define H263CU_PICFLAG_DISPOSABLE 8u
 
 typedef struct h263cu_pic { /* 32 bytes */
     uint32_t stream;        /* stream slot inside the context, < max_streams */

@@ -38,7 +38,8 @@ typedef struct h263cu_synth_params {
     uint32_t permille_overflow; /* per-mille of coded blocks whose runs overflow the zig-zag */
     uint32_t mv_mode;      /* 0 small vectors, 1 full range uniform, 2 biased across borders */
     uint32_t truncate_permille; /* per-mille of P pictures that end early (padding path) */
-    uint32_t reserved[4];
+    uint32_t pct_disposable;  /* Sorenson only: % of P pictures sent as disposable P pictures (type code 2) */
+    uint32_t reserved[3];
 } h263cu_synth_params;
 
 void h263cu_synth_default_params(h263cu_synth_params* p, uint32_t width, uint32_t height, uint32_t n_pictures,

@@ -590,7 +590,9 @@ Err decode_motion_vector(Reader& r, const Picture& pic, uint32_t running_options
 }
 
 // decode_macroblock (macroblock.rs:445-549)
-Err decode_macroblock(Reader& r, const Picture& pic, uint32_t running_options, Macroblock* out) {
+// decode_disposable: EXTENSION beyond the reference (ORC_OPT_DECODE_DISPOSABLE): a Sorenson disposable P picture is
+// parsed like a P picture; the reference itself fails it with UnimplementedDecoding (macroblock.rs:461-465).
+Err decode_macroblock(Reader& r, const Picture& pic, uint32_t running_options, Macroblock* out, bool decode_disposable = false) {
     size_t checkpoint = r.bits_read;
     Err e = ORC_OK;
     Macroblock mb;
@@ -610,7 +612,7 @@ Err decode_macroblock(Reader& r, const Picture& pic, uint32_t running_options, M
     const VlcCode* c;
     if (pic.picture_type == PT_I) {
         if ((e = r.read_vlc(g_trees[0], &c))) return fail(e);
-    } else if (pic.picture_type == PT_P) {
+    } else if (pic.picture_type == PT_P || (decode_disposable && pic.picture_type == PT_DISPOSABLE_P)) {
         if ((e = r.read_vlc(g_trees[1], &c))) return fail(e);
     } else {
         return fail(ORC_ERR_UNIMPLEMENTED_DECODING);
@@ -1211,6 +1213,9 @@ struct orc_state {
     bool has_last = false;
     bool has_reference = false;
     DecodedPicture last;
+    // EXTENSION (ORC_OPT_DECODE_DISPOSABLE): the last NON-disposable picture, which is what a disposable-aware decoder
+    // predicts from.  Unused (and never filled) without the option: the reference predicts from the last picture.
+    DecodedPicture reference;
     uint32_t running_options = 0;  // never updated by the reference (stays empty)
 
     bool trace = false;
@@ -1254,7 +1259,8 @@ Err decode_next_picture(orc_state* st, Reader& reader) {
     else
         return fail(ORC_ERR_PICTURE_FORMAT_MISSING);
 
-    const DecodedPicture* reference_picture = (st->has_reference && st->has_last) ? &st->last : nullptr;
+    const bool ext_disposable = (st->decoder_options & ORC_OPT_DECODE_DISPOSABLE) != 0;
+    const DecodedPicture* reference_picture = (st->has_reference && st->has_last) ? (ext_disposable ? &st->reference : &st->last) : nullptr;
 
     uint16_t ow, oh;
     if (!format.dims(&ow, &oh)) return fail(ORC_ERR_PICTURE_FORMAT_INVALID);
@@ -1287,7 +1293,7 @@ Err decode_next_picture(orc_state* st, Reader& reader) {
 
     for (;;) {
         Macroblock mb;
-        Err me = decode_macroblock(reader, np.header, next_running_options, &mb);
+        Err me = decode_macroblock(reader, np.header, next_running_options, &mb, ext_disposable);
         size_t pos_x = (macroblock_types.size() % mb_per_line) * 16;
         size_t pos_y = (macroblock_types.size() / mb_per_line) * 16;
         std::array<MotionVector, 4> motion_vectors{};
@@ -1410,7 +1416,10 @@ Err decode_next_picture(orc_state* st, Reader& reader) {
     // Reference bookkeeping (state.rs:464-483)
     if (np.header.picture_type == PT_I) st->has_reference = false;
     st->has_last = true;
-    if (np.header.picture_type != PT_DISPOSABLE_P) st->has_reference = true;
+    if (np.header.picture_type != PT_DISPOSABLE_P) {
+        st->has_reference = true;
+        if (ext_disposable) st->reference = np;  // a copy: `last` and `reference` part ways at the next disposable picture
+    }
     st->last = std::move(np);
     if (tr) {
         st->t_mb_type.swap(t_mb_type);

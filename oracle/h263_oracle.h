@@ -56,6 +56,12 @@ enum {
 /* DecoderOption bitflags (decoder/types.rs:3-18) */
 #define ORC_OPT_SORENSON_SPARK_BITSTREAM 1
 #define ORC_OPT_USE_SCALABILITY_MODE 2
+/* EXTENSION, not reference behaviour: decode Sorenson disposable P pictures (type code 2) like P pictures that
+ * never become a reference.  The reference fails them with UnimplementedDecoding (macroblock.rs:461-465) and, for
+ * the all-uncoded ones it does accept, predicts the next picture from them (get_reference_picture returns the LAST
+ * picture, state.rs:72-78).  With this bit the oracle predicts from the last NON-disposable picture instead; it is
+ * the checker of the product's H263CU_OPT_DECODE_DISPOSABLE and is pinned by no reference vector. */
+#define ORC_OPT_DECODE_DISPOSABLE 0x100
 
 /* PictureTypeCode as reported by orc_last_picture_info */
 #define ORC_PIC_I 0

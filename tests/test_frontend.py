@@ -124,3 +124,32 @@ def test_parse_step_threaded_matches_serial():
             assert np.array_equal(events[p["first_event"] : p["first_event"] + p["n_event_units"]], ev)
             k += 1
         assert k == len(pics)
+
+
+OPT_DISPOSABLE = 0x100  # H263CU_OPT_DECODE_DISPOSABLE / ORC_OPT_DECODE_DISPOSABLE: an extension beyond the reference
+
+
+def test_disposable_pictures_extension_and_reference_behaviour():
+    """Sorenson disposable P pictures (type code 2).  Without the extension bit product and oracle fail them exactly
+    like the reference (UnimplementedDecoding at the first coded macroblock, macroblock.rs:461-465) and the stream
+    state stays put; with it both parse them like P pictures, flag them, and keep predicting from the last
+    non-disposable picture."""
+    pk = synth.make_stream(176, 144, 10, 77, pct_disposable=50, mv_mode=1, pct_fourmv=10)
+    types = [int(frontend.peek_picture(p)["pic_type"]) for p in pk]
+    assert types[0] == _lib.PIC_I and _lib.PIC_DISPOSABLE_P in types and _lib.PIC_P in types
+    # reference behaviour: the first disposable picture is refused with error 17 by both
+    nmb, nev, nerr = compare_parse_with_oracle(pk, 1)
+    assert nerr >= 1
+    first = types.index(_lib.PIC_DISPOSABLE_P)
+    with pytest.raises(_lib.H263Error) as e:
+        ps = frontend.Parser(1)
+        for p in pk[: first + 1]:
+            ps.parse_picture(p)
+    assert e.value.code == -17
+    # extension: everything parses, identically in product and oracle
+    nmb, nev, nerr = compare_parse_with_oracle(pk, 1 | OPT_DISPOSABLE)
+    assert nerr == 0 and nmb == 10 * 99
+    ps = frontend.Parser(1 | OPT_DISPOSABLE)
+    for p, t in zip(pk, types):
+        pic, _, _ = ps.parse_picture(p)
+        assert bool(pic["flags"][0] & 8) == (t == _lib.PIC_DISPOSABLE_P)  # H263CU_PICFLAG_DISPOSABLE

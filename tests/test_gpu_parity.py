@@ -605,3 +605,48 @@ def test_resident_steps_as_one_cuda_graph():
     for s in steps:
         ctx.step_free(s)
     ctx.close()
+
+
+def test_disposable_p_pictures_are_shown_but_never_predicted_from():
+    """EXTENSION (H263CU_OPT_DECODE_DISPOSABLE): Sorenson disposable P pictures decode like P pictures, become the
+    stream's last picture, and the next picture still predicts from the last non-disposable one.  Bit exact against
+    the oracle run with the same extension, through the single-stream state, the batch path and a CUDA graph."""
+    opt = 1 | 0x100
+    pk = synth.make_stream(352, 288, 9, 91, pct_disposable=45, mv_mode=2, pct_fourmv=15)
+    types = [int(frontend.peek_picture(p)["pic_type"]) for p in pk]
+    assert types.count(_lib.PIC_DISPOSABLE_P) >= 2 and types.count(_lib.PIC_P) >= 2
+    # a disposable picture followed by a P picture must be in the stream, else the test shows nothing
+    assert any(a == _lib.PIC_DISPOSABLE_P and b == _lib.PIC_P for a, b in zip(types, types[1:]))
+    ref = oracle_decode_stream(pk, opt)
+    st = api.H263State(opt)
+    for i, p in enumerate(pk):
+        st.decode_next_picture(p)
+        y, cb, cr = st.get_last_picture().as_yuv()
+        assert np.array_equal(y, ref[i]["y"]) and np.array_equal(cb, ref[i]["cb"]) and np.array_equal(cr, ref[i]["cr"]), (i, types[i])
+        assert np.array_equal(st.get_last_rgba(), ref[i]["rgba"]), (i, types[i])
+    # without the extension the product refuses the picture like the reference does, and the stream carries on
+    st2 = api.H263State(1)
+    first = types.index(_lib.PIC_DISPOSABLE_P)
+    for p in pk[:first]:
+        st2.decode_next_picture(p)
+    with pytest.raises(_lib.H263Error) as e:
+        st2.decode_next_picture(pk[first])
+    assert e.value.code == -17
+    # resident steps + CUDA graph walk the same slot logic
+    ctx = api.Context(0, 1, 352, 288)
+    ps = frontend.Parser(opt)
+    steps = []
+    for p in pk:
+        pic, mbs, ev = ps.parse_picture(p)
+        steps.append(ctx.step_upload(pic, mbs, ev))
+    ctx.step_run(steps[0], _lib.OUT_RGBA)
+    g = ctx.graph_build(steps[1:], _lib.OUT_RGBA)
+    ctx.graph_launch(g)
+    ctx.sync()
+    y, cb, cr = ctx.read_yuv(0)
+    assert np.array_equal(y, ref[-1]["y"]) and np.array_equal(cb, ref[-1]["cb"]) and np.array_equal(cr, ref[-1]["cr"])
+    assert np.array_equal(ctx.read_rgba(0), ref[-1]["rgba"])
+    ctx.graph_free(g)
+    for s in steps:
+        ctx.step_free(s)
+    ctx.close()
