@@ -47,6 +47,11 @@ constexpr int WARP_MBS = 4;  // macroblocks per warp
 #ifndef H263_RGBA_TMA
 #define H263_RGBA_TMA 1
 #endif
+// BT.601 arithmetic: 0 = multiply-add + shift + saturating packs (v14), 1 = complemented terms clamped by VIADDMNMX.RELU,
+// 2 = 1 with the sample extraction as a dot product, 3 = 0 with extraction and shifts as dot products
+#ifndef H263_RGBA_MODE
+#define H263_RGBA_MODE 2
+#endif
 constexpr int CTA_WARPS = H263_CTA_WARPS;
 constexpr int CTA_THREADS = CTA_WARPS * 32;
 constexpr int WARP_BLOCKS = WARP_MBS * 6;
@@ -159,6 +164,7 @@ __device__ __forceinline__ int opaque(int v) {
     asm("" : "+r"(v));
     return v;
 }
+#if H263_RGBA_MODE == 0 || H263_RGBA_MODE == 3
 __device__ __forceinline__ CT chroma_terms_folded(int cb, int cr, int kr, int kg, int kb) {
     CT t;
     t.r = cr * kr + (32768 - 128 * 104597 - 16 * 76309);
@@ -166,9 +172,67 @@ __device__ __forceinline__ CT chroma_terms_folded(int cb, int cr, int kr, int kg
     t.b = cb * kb + (32768 - 128 * 132201 - 16 * 76309);
     return t;
 }
-__device__ __forceinline__ uint32_t rgba_px(int y, const CT& t) {
-    const int r = (y * 76309 + t.r) >> 16, g = (y * 76309 + t.g) >> 16, b = (y * 76309 + t.b) >> 16;
+#else
+// The same terms complemented, t' = 0xFFFFFF - t (kr, kg, kb arrive negated): with w = t' - 76309*y = 0xFFFFFF - x the
+// clamp of w to [0, 0xFFFFFF] carries 255 - clamp(x >> 16, 0, 255) in byte 2 and zero in byte 3 (rgba_px below).
+__device__ __forceinline__ CT chroma_terms_folded(int cb, int cr, int kr, int kg, int kb) {
+    CT t;
+    t.r = cr * kr + (0xFFFFFF - (32768 - 128 * 104597 - 16 * 76309));
+    t.g = cr * kg + (cb * 25675 + (0xFFFFFF - (32768 + 128 * 53279 + 128 * 25675 - 16 * 76309)));
+    t.b = cb * kb + (0xFFFFFF - (32768 - 128 * 132201 - 16 * 76309));
+    return t;
+}
+#endif
+#if H263_RGBA_MODE == 0
+// yw = the four luma samples of the row as bytes, k = which one
+__device__ __forceinline__ uint32_t rgba_px(uint32_t yw, int k, int ky, const CT& t) {
+    const int y = (int)(__byte_perm(yw, 0, 0x4440 + k));
+    const int r = (y * ky + t.r) >> 16, g = (y * ky + t.g) >> 16, b = (y * ky + t.b) >> 16;
     return pack_sat(g, r, pack_sat(255, b, 0));
+}
+#elif H263_RGBA_MODE == 3
+// everything but the saturating packs on the multiply pipe: sample extraction and the >> 16 are dot products
+// (IDP.4A with a one-hot selector, IDP.2A picking the signed upper half)
+__device__ __forceinline__ uint32_t rgba_px(uint32_t yw, int k, int ky, const CT& t) {
+    const int y = (int)__dp4a(yw, 1u << (8 * k), 0u);
+    const int r = __dp2a_hi(y * ky + t.r, 0x01000000, 0), g = __dp2a_hi(y * ky + t.g, 0x01000000, 0), b = __dp2a_hi(y * ky + t.b, 0x01000000, 0);
+    return pack_sat(g, r, pack_sat(255, b, 0));
+}
+#else
+// Complemented form: w_c = clamp(t'_c - 76309*y, 0, 0xFFFFFF) = clamp(0xFFFFFF - x_c) is ONE instruction per channel
+// (VIADDMNMX.RELU) and holds 255 - C in byte 2, 0 in byte 3: for x < 0 it is 0xFFFFFF (C = 0), for x > 0xFFFFFF it is
+// 0 (C = 255), and in between 0xFFFFFF - x is the 24-bit complement of x.  One byte permute gathers (~R, ~G, 0, 0), one
+// LOP3 merges ~B and inverts: (R, G, B, 0xFF).  ky arrives negated.
+__device__ __forceinline__ uint32_t rgba_px(uint32_t yw, int k, int ky, const CT& t) {
+#if H263_RGBA_MODE == 1
+    const int y = (int)(__byte_perm(yw, 0, 0x4440 + k));
+#else
+    const int y = (int)__dp4a(yw, 1u << (8 * k), 0u);  // sample extraction on the multiply pipe
+#endif
+    const int nyk = opaque(y * ky);  // kept apart from the additions: they ride on the clamp instruction
+    const uint32_t wr = (uint32_t)__viaddmin_s32_relu(nyk, t.r, 0xFFFFFF), wg = (uint32_t)__viaddmin_s32_relu(nyk, t.g, 0xFFFFFF),
+                   wb = (uint32_t)__viaddmin_s32_relu(nyk, t.b, 0xFFFFFF);
+    const uint32_t rg = __byte_perm(wr, wg, 0x3362);
+    uint32_t px;  // ~(rg | (wb & 0xFFFF0000)) as ONE LOP3 (the compiler splits the inversion off)
+    asm("lop3.b32 %0, %1, %2, 0xFFFF0000, 0x07;" : "=r"(px) : "r"(rg), "r"(wb));
+    return px;
+}
+#endif
+
+// One step of an inclusive warp prefix sum: v += v of the lane d below, where there is one.  The shuffle's own
+// predicate (source lane in range) guards the addition: two instructions per step instead of shuffle + compare +
+// select + add.
+__device__ __forceinline__ uint32_t scan_up_step(uint32_t v, int d) {
+    asm volatile("{ .reg .pred p; .reg .b32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }" : "+r"(v) : "r"(d));
+    return v;
+}
+// The same for a segmented sum: the addition happens when the lane d below belongs to the same segment (dist = lanes
+// between this lane and the head of its segment).
+__device__ __forceinline__ int seg_scan_up_step(int v, int d, int dist) {
+    asm volatile("{ .reg .pred p; .reg .b32 t; shfl.sync.up.b32 t, %0, %1, 0, 0xffffffff; setp.ge.s32 p, %2, %1; @p add.s32 %0, %0, t; }"
+                 : "+r"(v)
+                 : "r"(d), "r"(dist));
+    return v;
 }
 
 // keep the low `keep` bytes (0..4) of a, take the rest from b
@@ -239,20 +303,24 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             int mvx, mvy, bx, sy, pitch;
             uint32_t base;
             bool in_range;
+            // Vectors of a step that runs this instantiation lie in [-32, 31] (the parser's halfpel_decode wraps into
+            // that range, mvd_pred.rs:70-117; caller-built side info is checked on the host and a picture with a longer
+            // vector takes the WIDE_MV instantiation), so nothing is clamped here.  Signed bytes come out of the record
+            // words as dot products with a one-hot selector (IDP.4A on the multiply pipe, not the ALU).
             if (bb < 4) {
-                // mv[bb] = bytes 2bb, 2bb+1 of (w4, w5), sign-extended
-                mvx = (int)(int8_t)__byte_perm(w4, w5, 0x4440u + 2u * (uint32_t)bb), mvy = (int)(int8_t)__byte_perm(w4, w5, 0x4441u + 2u * (uint32_t)bb);
-                if (!WIDE_MV) mvx = max(min(mvx, 31), -32), mvy = max(min(mvy, 31), -32);
+                // mv[bb] = bytes 2bb, 2bb+1 of (w4, w5)
+                const int m = (int)((bb < 2 ? w4 : w5) >> (16 * (bb & 1)));
+                mvx = __dp4a(m, 0x00000001, 0), mvy = __dp4a(m, 0x00000100, 0);
                 in_range = mvx >= -32 && mvx <= 31 && mvy >= -32 && mvy <= 31;
                 bx = mbx * 16 + (bb & 1) * 8 + (mvx >> 1), sy = mby * 16 + (bb >> 1) * 8 + (mvy >> 1);
                 pitch = PY ? PY : P.pitch_y, base = P.ref_y4;
             } else {
-                // both chroma blocks use the average of the four luma vectors (gather.rs:182, types.rs:759-768);
+                // both chroma blocks use the average of the four luma vectors (gather.rs:182, types.rs:759-768):
+                // average_sum_of_mvs(s) = 2 (s >> 4) + [s & 15 > 2] + [s & 15 >= 14] = ((s + 13) >> 4) + ((s + 2) >> 4);
                 // the chroma planes are interleaved: sample x of a row sits at byte 2x (Cb) and 2x + 1 (Cr)
-                const int sumx = (int8_t)byte_of(w4, 0) + (int8_t)byte_of(w4, 2) + (int8_t)byte_of(w5, 0) + (int8_t)byte_of(w5, 2);
-                const int sumy = (int8_t)byte_of(w4, 1) + (int8_t)byte_of(w4, 3) + (int8_t)byte_of(w5, 1) + (int8_t)byte_of(w5, 3);
-                mvx = average_sum_of_mvs(sumx), mvy = average_sum_of_mvs(sumy);
-                if (!WIDE_MV) mvx = max(min(mvx, 15), -16), mvy = max(min(mvy, 15), -16);
+                const int sx = __dp4a((int)w5, 0x00010001, __dp4a((int)w4, 0x00010001, 13));
+                const int sy13 = __dp4a((int)w5, 0x01000100, __dp4a((int)w4, 0x01000100, 13));
+                mvx = (sx >> 4) + ((sx - 11) >> 4), mvy = (sy13 >> 4) + ((sy13 - 11) >> 4);
                 in_range = mvx >= -16 && mvx <= 15 && mvy >= -16 && mvy <= 15;
                 bx = 2 * (mbx * 8 + (mvx >> 1)), sy = mby * 8 + (mvy >> 1);
                 pitch = PC ? PC : P.pitch_c, base = P.ref_c4;
@@ -292,10 +360,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         n_slots = __popc(coded_mask);
         uint32_t ev_incl = nev;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t x = __shfl_up_sync(FULL, ev_incl, d);
-            if (lane >= d) ev_incl += x;
-        }
+        for (int d = 1; d < 32; d <<= 1) ev_incl = scan_up_step(ev_incl, d);
         // events of the blocks before this one inside the macroblock
         const uint32_t before = (ev_incl - nev) - __shfl_sync(FULL, ev_incl - nev, bm * 6);
         if (coded) {
@@ -371,12 +436,9 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     }
                     v = run + 1;
                 }
-                const int seg0 = max(seg, 0);
+                const int dist = lane - max(seg, 0);
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int x = __shfl_up_sync(FULL, v, d);
-                    if (lane - d >= seg0) v += x;
-                }
+                for (int d = 1; d < 32; d <<= 1) v = seg_scan_up_step(v, d, dist);
                 if (seg < 0) v += (int)carry;
                 carry = (uint32_t)__shfl_sync(FULL, v, 31);
                 if (act) {
@@ -776,7 +838,11 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         __syncwarp();  // every lane has read its residuals: the RGBA tile may overwrite them
 #endif
         if (flags & MBF_RGBA) {
-            const int kr = opaque(104597), kg = opaque(-53279), kb = opaque(132201);
+#if H263_RGBA_MODE == 0 || H263_RGBA_MODE == 3
+            const int kr = opaque(104597), kg = opaque(-53279), kb = opaque(132201), ky = opaque(76309);
+#else
+            const int kr = opaque(-104597), kg = opaque(53279), kb = opaque(-132201), ky = opaque(-76309);
+#endif
 #if H263_RGBA_TMA
             uint8_t* const stage = reinterpret_cast<uint8_t*>(&G);
 #else
@@ -785,16 +851,22 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
 #endif
 #pragma unroll
             for (int c2 = 0; c2 < 4; c2++) {
+#if H263_RGBA_MODE >= 2
+                // cw = (cb0, cr0, cb1, cr1): the samples come out as dot products with a one-hot selector (multiply pipe)
+                const CT t0 = chroma_terms_folded((int)__dp4a(cw[c2], 1u, 0u), (int)__dp4a(cw[c2], 1u << 8, 0u), kr, kg, kb);
+                const CT t1 = chroma_terms_folded((int)__dp4a(cw[c2], 1u << 16, 0u), (int)__dp4a(cw[c2], 1u << 24, 0u), kr, kg, kb);
+#else
                 const CT t0 = chroma_terms_folded((int)(cbp[c2] & 0xFFFFu), (int)(crp[c2] & 0xFFFFu), kr, kg, kb);
                 const CT t1 = chroma_terms_folded((int)(cbp[c2] >> 16), (int)(crp[c2] >> 16), kr, kg, kb);
+#endif
 #pragma unroll
                 for (int rr = 0; rr < 2; rr++) {
                     const int r = c2 * 2 + rr;
                     uint4 px;
-                    px.x = rgba_px((int)(ylo[r] & 0xFFFFu), t0);
-                    px.y = rgba_px((int)(ylo[r] >> 16), t0);
-                    px.z = rgba_px((int)(yhi[r] & 0xFFFFu), t1);
-                    px.w = rgba_px((int)(yhi[r] >> 16), t1);
+                    px.x = rgba_px(yw[r], 0, ky, t0);
+                    px.y = rgba_px(yw[r], 1, ky, t0);
+                    px.z = rgba_px(yw[r], 2, ky, t1);
+                    px.w = rgba_px(yw[r], 3, ky, t1);
 #if H263_RGBA_TMA
                     *reinterpret_cast<uint4*>(stage + stage_offset(mbq, rgrp * 8 + r, cg)) = px;
 #else
