@@ -47,10 +47,11 @@ constexpr int WARP_MBS = 4;  // macroblocks per warp
 #ifndef H263_RGBA_TMA
 #define H263_RGBA_TMA 1
 #endif
-// BT.601 arithmetic: 0 = multiply-add + shift + saturating packs (v14), 1 = complemented terms clamped by VIADDMNMX.RELU,
-// 2 = 1 with the sample extraction as a dot product, 3 = 0 with extraction and shifts as dot products
+// BT.601 arithmetic: 0 = multiply-add + shift + saturating packs (v14), 1 = complemented terms, one clamp per channel,
+// 2 = 1 with the sample extraction as a dot product, 3 = 0 with extraction and shifts as dot products, 4 = 2 with green
+// and blue as differences from red added inside the clamp instruction (profiles/r02_variants.txt)
 #ifndef H263_RGBA_MODE
-#define H263_RGBA_MODE 2
+#define H263_RGBA_MODE 4
 #endif
 constexpr int CTA_WARPS = H263_CTA_WARPS;
 constexpr int CTA_THREADS = CTA_WARPS * 32;
@@ -180,6 +181,12 @@ __device__ __forceinline__ CT chroma_terms_folded(int cb, int cr, int kr, int kg
     t.r = cr * kr + (0xFFFFFF - (32768 - 128 * 104597 - 16 * 76309));
     t.g = cr * kg + (cb * 25675 + (0xFFFFFF - (32768 + 128 * 53279 + 128 * 25675 - 16 * 76309)));
     t.b = cb * kb + (0xFFFFFF - (32768 - 128 * 132201 - 16 * 76309));
+#if H263_RGBA_MODE == 4
+    // green and blue as differences from red: the pixel's multiply-add then happens once (red) and the other two
+    // channels add their difference inside the clamp instruction (VIADDMNMX.RELU)
+    t.g = cr * (kg - kr) + (cb * 25675 + ((32768 - 128 * 104597) - (32768 + 128 * 53279 + 128 * 25675)));
+    t.b = cb * kb + (cr * -kr + ((32768 - 128 * 104597) - (32768 - 128 * 132201)));
+#endif
     return t;
 }
 #endif
@@ -209,9 +216,15 @@ __device__ __forceinline__ uint32_t rgba_px(uint32_t yw, int k, int ky, const CT
 #else
     const int y = (int)__dp4a(yw, 1u << (8 * k), 0u);  // sample extraction on the multiply pipe
 #endif
-    const int nyk = opaque(y * ky);  // kept apart from the additions: they ride on the clamp instruction
+#if H263_RGBA_MODE == 4
+    const int xr = y * ky + t.r;
+    const uint32_t wr = (uint32_t)__vimin_s32_relu(xr, 0xFFFFFF), wg = (uint32_t)__viaddmin_s32_relu(xr, t.g, 0xFFFFFF),
+                   wb = (uint32_t)__viaddmin_s32_relu(xr, t.b, 0xFFFFFF);
+#else
+    const int nyk = opaque(y * ky);  // the compiler folds the additions into three multiply-adds + three clamps
     const uint32_t wr = (uint32_t)__viaddmin_s32_relu(nyk, t.r, 0xFFFFFF), wg = (uint32_t)__viaddmin_s32_relu(nyk, t.g, 0xFFFFFF),
                    wb = (uint32_t)__viaddmin_s32_relu(nyk, t.b, 0xFFFFFF);
+#endif
     const uint32_t rg = __byte_perm(wr, wg, 0x3362);
     uint32_t px;  // ~(rg | (wb & 0xFFFF0000)) as ONE LOP3 (the compiler splits the inversion off)
     asm("lop3.b32 %0, %1, %2, 0xFFFF0000, 0x07;" : "=r"(px) : "r"(rg), "r"(wb));
