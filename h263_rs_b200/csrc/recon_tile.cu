@@ -793,58 +793,6 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             }
         }
 
-        // ---- plane stores (+ border replication for the next picture's prediction) ----
-        if (unit_ok && !(H263_ABLATE & 8)) {
-            const uint32_t pitch_y = pitch_y4 * 4, pitch_c = pitch_c4 * 4;
-            uint8_t* py = pools.y + (size_t)(ma.x + (uint32_t)(rgrp * 8) * pitch_y4 + (uint32_t)cg) * 4;
-            uint8_t* pc = pools.c + (size_t)(ma.y + (uint32_t)(rgrp * 4) * pitch_c4 + (uint32_t)cg) * 4;
-#pragma unroll
-            for (int r = 0; r < 8; r++) *reinterpret_cast<uint32_t*>(py + r * pitch_y) = yw[r];
-#pragma unroll
-            for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t*>(pc + r * pitch_c) = cw[r];
-            // edges this lane owns: left for cg = 0, right for cg = 3, top for rgrp = 0, bottom for rgrp = 1.
-            // 16 luma pixels / 8 CbCr pairs (16 bytes) of extension on each side, 16 / 8 rows above and below.
-            const bool e_left = (flags & MBF_LEFT) && cg == 0, e_right = (flags & MBF_RIGHT) && cg == 3;
-            const bool e_top = (flags & MBF_TOP) && rgrp == 0, e_bot = (flags & MBF_BOTTOM) && rgrp == 1;
-            if (e_left | e_right | e_top | e_bot) {
-                const ptrdiff_t side = e_left ? -16 : 4;  // of the 16 border bytes, from the lane's word
-                if (e_left | e_right) {
-#pragma unroll
-                    for (int r = 0; r < 8; r++) {
-                        const uint32_t v = __byte_perm(yw[r], 0, e_left ? 0x0000 : 0x3333);
-                        *reinterpret_cast<uint4*>(py + r * pitch_y + side) = make_uint4(v, v, v, v);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const uint32_t v = __byte_perm(cw[r], 0, e_left ? 0x1010 : 0x3232);
-                        *reinterpret_cast<uint4*>(pc + r * pitch_c + side) = make_uint4(v, v, v, v);
-                    }
-                }
-                if (e_top | e_bot) {
-                    // vertical extension, including the corners when the lane also sits on a vertical edge
-                    const bool corner = e_left | e_right;
-                    const uint32_t v = e_top ? yw[0] : yw[7];
-                    uint8_t* rowp = e_top ? py : py + 7 * pitch_y;
-                    const ptrdiff_t dir = e_top ? -(ptrdiff_t)pitch_y : (ptrdiff_t)pitch_y;
-                    const uint32_t vc = __byte_perm(v, 0, e_left ? 0x0000 : 0x3333);
-                    for (int k = 1; k <= 16; k++) {
-                        uint8_t* d = rowp + k * dir;
-                        *reinterpret_cast<uint32_t*>(d) = v;
-                        if (corner) *reinterpret_cast<uint4*>(d + side) = make_uint4(vc, vc, vc, vc);
-                    }
-                    const uint32_t c = e_top ? cw[0] : cw[3];
-                    uint8_t* rc = e_top ? pc : pc + 3 * pitch_c;
-                    const ptrdiff_t cdir = e_top ? -(ptrdiff_t)pitch_c : (ptrdiff_t)pitch_c;
-                    const uint32_t cc = __byte_perm(c, 0, e_left ? 0x1010 : 0x3232);
-                    for (int k = 1; k <= 8; k++) {
-                        uint8_t* d = rc + k * cdir;
-                        *reinterpret_cast<uint32_t*>(d) = c;
-                        if (corner) *reinterpret_cast<uint4*>(d + side) = make_uint4(cc, cc, cc, cc);
-                    }
-                }
-            }
-        }
-
         // ---- BT.601 RGBA (bt601.rs:12-59): 4 pixels per row = 16 bytes; chroma row r >> 1, sample 0 for pixels 0-1
         // and sample 1 for pixels 2-3, all in this lane's registers ----
 #if H263_RGBA_TMA
@@ -904,10 +852,67 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                              "r"((int)(W.mb[lane][5] * 64u)), "r"((int)W.mb[lane][2])
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                // the tile must stay in place until the store has read it
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
         }
+#endif
+
+        // (the plane stores come after the RGBA tile has been handed to the TMA unit, so that the unit reads the tile
+        // while the warp is still busy: a warp may not leave before that read is over)
+        // ---- plane stores (+ border replication for the next picture's prediction) ----
+        if (unit_ok && !(H263_ABLATE & 8)) {
+            const uint32_t pitch_y = pitch_y4 * 4, pitch_c = pitch_c4 * 4;
+            uint8_t* py = pools.y + (size_t)(ma.x + (uint32_t)(rgrp * 8) * pitch_y4 + (uint32_t)cg) * 4;
+            uint8_t* pc = pools.c + (size_t)(ma.y + (uint32_t)(rgrp * 4) * pitch_c4 + (uint32_t)cg) * 4;
+#pragma unroll
+            for (int r = 0; r < 8; r++) *reinterpret_cast<uint32_t*>(py + r * pitch_y) = yw[r];
+#pragma unroll
+            for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t*>(pc + r * pitch_c) = cw[r];
+            // edges this lane owns: left for cg = 0, right for cg = 3, top for rgrp = 0, bottom for rgrp = 1.
+            // 16 luma pixels / 8 CbCr pairs (16 bytes) of extension on each side, 16 / 8 rows above and below.
+            const bool e_left = (flags & MBF_LEFT) && cg == 0, e_right = (flags & MBF_RIGHT) && cg == 3;
+            const bool e_top = (flags & MBF_TOP) && rgrp == 0, e_bot = (flags & MBF_BOTTOM) && rgrp == 1;
+            if (e_left | e_right | e_top | e_bot) {
+                const ptrdiff_t side = e_left ? -16 : 4;  // of the 16 border bytes, from the lane's word
+                if (e_left | e_right) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const uint32_t v = __byte_perm(yw[r], 0, e_left ? 0x0000 : 0x3333);
+                        *reinterpret_cast<uint4*>(py + r * pitch_y + side) = make_uint4(v, v, v, v);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const uint32_t v = __byte_perm(cw[r], 0, e_left ? 0x1010 : 0x3232);
+                        *reinterpret_cast<uint4*>(pc + r * pitch_c + side) = make_uint4(v, v, v, v);
+                    }
+                }
+                if (e_top | e_bot) {
+                    // vertical extension, including the corners when the lane also sits on a vertical edge
+                    const bool corner = e_left | e_right;
+                    const uint32_t v = e_top ? yw[0] : yw[7];
+                    uint8_t* rowp = e_top ? py : py + 7 * pitch_y;
+                    const ptrdiff_t dir = e_top ? -(ptrdiff_t)pitch_y : (ptrdiff_t)pitch_y;
+                    const uint32_t vc = __byte_perm(v, 0, e_left ? 0x0000 : 0x3333);
+                    for (int k = 1; k <= 16; k++) {
+                        uint8_t* d = rowp + k * dir;
+                        *reinterpret_cast<uint32_t*>(d) = v;
+                        if (corner) *reinterpret_cast<uint4*>(d + side) = make_uint4(vc, vc, vc, vc);
+                    }
+                    const uint32_t c = e_top ? cw[0] : cw[3];
+                    uint8_t* rc = e_top ? pc : pc + 3 * pitch_c;
+                    const ptrdiff_t cdir = e_top ? -(ptrdiff_t)pitch_c : (ptrdiff_t)pitch_c;
+                    const uint32_t cc = __byte_perm(c, 0, e_left ? 0x1010 : 0x3232);
+                    for (int k = 1; k <= 8; k++) {
+                        uint8_t* d = rc + k * cdir;
+                        *reinterpret_cast<uint32_t*>(d) = c;
+                        if (corner) *reinterpret_cast<uint4*>(d + side) = make_uint4(cc, cc, cc, cc);
+                    }
+                }
+            }
+        }
+
+#if H263_RGBA_TMA
+        // the tile must stay in place until the stores have read it
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #endif
     }
 }
