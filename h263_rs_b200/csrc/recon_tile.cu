@@ -73,7 +73,7 @@ constexpr uint32_t BF_SLOW = 1u << 4;  // the vector leaves the replicated borde
 struct __align__(16) WarpStage {
     uint32_t res[WARP_BLOCKS][RES_WORDS];  // per slot: residual rows, s16 row-major (row j = words 4j..4j+3)
     uint32_t evbuf[EV_CAP];                // walked events of the slots in flight: lin[5:0] | dropped[15] | value[31:16]
-    uint2 slotdesc[WARP_BLOCKS];           // x = first event unit (absolute), y = nev | quant<<8 | wide<<13 | inter<<14 | block<<16 | dc<<24
+    uint2 slotdesc[WARP_BLOCKS];           // x = first event unit (absolute), y = nev | quant<<8 | wide<<13 | inter<<14 | chroma<<15 | block<<16 | dc<<24
     uint32_t pad[16];
 };
 static_assert(sizeof(WarpStage) == STAGE_BYTES, "the RGBA tile aliases exactly this");
@@ -126,17 +126,19 @@ __device__ __forceinline__ int round_q(float q, float m) { return __float2int_rz
 // ---- half-pel interpolation in 16-bit lanes -------------------------------------------------
 // A prediction row of a lane is 4 samples (luma: 4 pixels; chroma: the CbCr pairs of 2 samples) that start `sh`
 // bits into the aligned word pair (w0, w1); the horizontal neighbours start `shb` bits in (sh, or sh + one sample).
-// Returns a + b per sample in two words of two 16-bit lanes.  With shb == sh this is 2a.  SEL_LO / SEL_HI pick the
-// samples of each word: luma (p0,p1) (p2,p3), chroma (cb0,cb1) (cr0,cr1).
+// Returns a + b per sample in two words of two 16-bit lanes.  With shb == sh this is 2a.
 struct RowSum {
     uint32_t lo, hi;
 };
-template <uint32_t SEL_LO, uint32_t SEL_HI>
+// lo = the even samples (bytes 0 and 2 of the four), hi = the odd ones: luma (p0, p2) (p1, p3), chroma (cb0, cb1) (cr0, cr1).
+// Only the odd samples are unpacked: a word is E + 256 O in terms of its even / odd lane words, so the even lanes of
+// a + b are (a + b) - 256 (O_a + O_b) -- exact modulo 2^32, the true lane sums are below 2^32 -- one multiply-add on
+// the multiply pipe instead of two byte permutes on the ALU.
 __device__ __forceinline__ RowSum row_sum4(uint32_t w0, uint32_t w1, int sh, int shb) {
     const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_rc(w0, w1, shb);
     RowSum h;
-    h.lo = __byte_perm(a, 0, SEL_LO) + __byte_perm(b, 0, SEL_LO);
-    h.hi = __byte_perm(a, 0, SEL_HI) + __byte_perm(b, 0, SEL_HI);
+    h.hi = __byte_perm(a, 0, 0x4341) + __byte_perm(b, 0, 0x4341);
+    h.lo = (a + b) - 256u * h.hi;
     return h;
 }
 // (top * (2 - iy) + bottom * iy + 2) >> 2 per 16-bit lane: with iy == 0 and ix == 0 this is exactly the sample,
@@ -247,6 +249,9 @@ __device__ __forceinline__ int seg_scan_up_step(int v, int d, int dist) {
                  : "r"(d), "r"(dist));
     return v;
 }
+
+// Two words of two 16-bit lanes holding bytes (e0, e1) and (o0, o1) -> the bytes (e0, o0, e1, o1): o * 256 + e
+__device__ __forceinline__ uint32_t mad_pack(uint32_t o, uint32_t e) { return o * 256u + e; }
 
 // keep the low `keep` bytes (0..4) of a, take the rest from b
 __device__ __forceinline__ uint32_t merge_bytes(uint32_t a, uint32_t b, int keep) {
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             const uint32_t first = P.first_event + w0 + (wide ? 2 * before : before);
             const uint32_t quant = (w2 >> 8) & 31u;
             G.slotdesc[pos] = make_uint2(first, nev | (quant << 8) | (wide ? 1u << 13 : 0u) | (inter ? 1u << 14 : 0u) |
-                                                    ((uint32_t)lane << 16) | (code << 24));
+                                                    (bb >= 4 ? 1u << 15 : 0u) | ((uint32_t)lane << 16) | (code << 24));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(events + first));
         } else if (bvalid) {
             // no coefficients: Dc(level) when an intra DC is present, else Zero (rle.rs:94-104)
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         const float bt0 = basis[0 * 8 + t], bt1 = basis[1 * 8 + t], bt2 = basis[2 * 8 + t], bt3 = basis[3 * 8 + t],
                     bt4 = basis[4 * 8 + t], bt5 = basis[5 * 8 + t], bt6 = basis[6 * 8 + t], bt7 = basis[7 * 8 + t];
         float* c = W.coef[g];
+        const int tperm = (t & 4) | ((t & 1) << 1) | ((t >> 1) & 1);
         // lane = slot for the per-slot steps
         if (H263_ABLATE & 1) n_slots = 0;
         const bool is_slot = lane < n_slots;
@@ -575,7 +581,9 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     // (idct.rs:191-194); the first clamp cannot change the result of the second (prediction in
                     // [0, 255]), and |value| <= 2048 * (sum_x |B[x][i]|)^2 / 4 < 14300 fits the s16 that carries it,
                     // so only the saturating add of phase 3 clamps.
-                    uint16_t* rrow = reinterpret_cast<uint16_t*>(&G.res[sl][0]) + t;
+                    // luma slots keep the columns of each group of four as (0, 2, 1, 3): the two words a lane of phase 3
+                    // reads per row are then its even and its odd samples, the split its registers use
+                    uint16_t* rrow = reinterpret_cast<uint16_t*>(&G.res[sl][0]) + ((sd.y & 0x8000u) ? t : tperm);
                     if (any_vert) {  // rare: a block with coefficients in its first column only
                         const float m = vert ? H263_B00 : 1.0f;
 #pragma unroll
@@ -607,7 +615,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         const int lb = rgrp * 2 + (cg >> 1);  // luma block of this lane
         const int bl = mbi * 6 + lb, bc = mbi * 6 + 4;
 
-        uint32_t ylo[8], yhi[8];  // luma rows: samples (p0, p1) and (p2, p3) in 16-bit lanes
+        uint32_t ylo[8], yhi[8];  // luma rows: samples (p0, p2) and (p1, p3) in 16-bit lanes (even / odd, like Cb / Cr below)
         uint32_t cbp[4], crp[4];  // chroma rows: (cb0, cb1) and (cr0, cr1)
         if (flags & MBF_INTER) {
             const uint32_t fl = W.bf[bl], fc = W.bf[bc];
@@ -628,7 +636,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                         w0 = __ldg(p);
                         if (second) w1 = __ldg(p + 1);
                     }
-                    hs[r] = row_sum4<0x4140, 0x4342>(w0, w1, sh, shb);
+                    hs[r] = row_sum4(w0, w1, sh, shb);
                 }
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
@@ -648,7 +656,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     uint32_t s[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) s[k] = mc_fetch1(P.ref[0], P.pitch_y, 1, P.w, P.h, x0 + k, y0 + r, mvx, mvy);
-                    ylo[r] = s[0] | (s[1] << 16), yhi[r] = s[2] | (s[3] << 16);
+                    ylo[r] = s[0] | (s[2] << 16), yhi[r] = s[1] | (s[3] << 16);
                 }
             }
             if (!WIDE_MV || !(fc & BF_SLOW)) {
@@ -665,7 +673,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                         w0 = __ldg(p);
                         if (second) w1 = __ldg(p + 1);
                     }
-                    hs[r] = row_sum4<0x4240, 0x4341>(w0, w1, sh, shb);
+                    hs[r] = row_sum4(w0, w1, sh, shb);
                 }
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
@@ -708,7 +716,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     yhi[r] = __viaddmin_s16x2_relu(yhi[r], dd, 0x00FF00FFu);
                 }
             } else if (cls != CLS_ZERO) {
-                // columns 4(cg & 1) .. +3 of the slot's rows: two words per row
+                // columns 4(cg & 1) .. +3 of the slot's rows, stored as (0, 2), (1, 3): two words per row
                 const uint2* c = reinterpret_cast<const uint2*>(&G.res[(m >> 3) & 31u][2 * (cg & 1)]);
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
@@ -738,9 +746,9 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         // ---- plane words: luma (p0 p1 p2 p3), chroma (cb0 cr0 cb1 cr1) ----
         uint32_t yw[8], cw[4];
 #pragma unroll
-        for (int r = 0; r < 8; r++) yw[r] = __byte_perm(ylo[r], yhi[r], 0x6420);
+        for (int r = 0; r < 8; r++) yw[r] = mad_pack(yhi[r], ylo[r]);
 #pragma unroll
-        for (int r = 0; r < 4; r++) cw[r] = __byte_perm(cbp[r], crp[r], 0x6240);
+        for (int r = 0; r < 4; r++) cw[r] = mad_pack(crp[r], cbp[r]);
         if constexpr (EDGE) {
             const uint32_t ed = mv.w;
             const int vw = (int)(ed & 15u), vh = (int)((ed >> 4) & 15u), cvw = (int)((ed >> 8) & 7u), cvh = (int)((ed >> 12) & 7u);
