@@ -47,6 +47,10 @@ constexpr int WARP_MBS = 4;  // macroblocks per warp
 #ifndef H263_RGBA_TMA
 #define H263_RGBA_TMA 1
 #endif
+// 1 = L2 prefetch of the prediction rows right after phase 0
+#ifndef H263_PREFETCH_PRED
+#define H263_PREFETCH_PRED 0
+#endif
 // BT.601 arithmetic: 0 = multiply-add + shift + saturating packs (v14), 1 = complemented terms, one clamp per channel,
 // 2 = 1 with the sample extraction as a dot product, 3 = 0 with extraction and shifts as dot products, 4 = 2 with green
 // and blue as differences from red added inside the clamp instruction (profiles/r02_variants.txt)
@@ -396,6 +400,25 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         }
     }
     __syncwarp();
+
+#if H263_PREFETCH_PRED
+    // The prediction rows are read in phase 3, one event walk and one transform from here: ask the L2 for them now
+    // (lane = 4 luma columns x 8 rows as in phase 3; the request of a lane covers the sector its words lie in).
+    {
+        const int mbq = lane >> 3, rgrp = (lane >> 2) & 1, cg = lane & 3;
+        const int mbi = mbq < n_w ? mbq : 0;
+        if (W.mb[mbi][3] & MBF_INTER) {
+            const uint32_t pitch_y4 = PY ? PY / 4 : (W.mb[mbi][4] & 0xFFFFu) >> 2, pitch_c4 = PC ? PC / 4 : W.mb[mbi][4] >> 18;
+            const int lb = rgrp * 2 + (cg >> 1);
+            const uint32_t* sy = reinterpret_cast<const uint32_t*>(pools.y) + W.bd[mbi * 6 + lb] + (uint32_t)(cg & 1);
+            const uint32_t* sc = reinterpret_cast<const uint32_t*>(pools.c) + W.bd[mbi * 6 + 4] + (uint32_t)cg + (uint32_t)(rgrp * 4) * pitch_c4;
+#pragma unroll
+            for (int r = 0; r < 9; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(sy + (uint32_t)r * pitch_y4));
+#pragma unroll
+            for (int r = 0; r < 5; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc + (uint32_t)r * pitch_c4));
+        }
+    }
+#endif
 
     // ================= phases 1 + 2, per chunk of slots whose events fit the event buffer ==========
     // (one chunk unless the four macroblocks hold more than EV_CAP events)
