@@ -31,25 +31,27 @@ namespace h263dev {
 namespace {
 
 constexpr int WARP_MBS = 4;  // macroblocks per warp
-#ifndef H263_CTA_WARPS
-#define H263_CTA_WARPS 4  // without a CTA barrier a CTA is just a group of warps: 4 beat 8 by 1-2 % (shorter tails)
+// Warps per CTA and CTAs per SM.  Without a CTA barrier a CTA is just a group of warps.  The instantiations for the
+// standard picture formats (compile-time pitches, no edge fix-up, no clamped prediction) keep less per warp in shared
+// memory (WarpTailT<true>) and compile to 56 registers: 7 CTAs of 5 warps = 35 warps per SM inside the 196 KB
+// carve-out, which leaves the L1 in place; the others run 8 CTAs of 4 warps at 64 registers.  The kernel gains about 5 %
+// per extra CTA of 4 warps (profiles/r02_variants.txt); 4 warps beat 8 by 2 % (shorter tails).
+#ifndef H263_STD_WARPS
+#define H263_STD_WARPS 5
 #endif
+#ifndef H263_STD_CTAS
+#define H263_STD_CTAS 7
+#endif
+constexpr int GEN_WARPS = 4, GEN_CTAS = 8;
 // Ablation builds for time attribution (results are wrong by design): 1 = no event walk / transform,
 // 2 = no prediction loads (every macroblock treated as intra), 4 = no RGBA, 8 = no plane stores,
 // 16 = RGBA computed but not stored.
 #ifndef H263_ABLATE
 #define H263_ABLATE 0
 #endif
-#ifndef H263_MIN_CTAS
-#define H263_MIN_CTAS (32 / H263_CTA_WARPS)
-#endif
 // 1 = RGBA through the shared-memory tile + TMA tensor stores, 0 = one 128-bit global store per lane and row
 #ifndef H263_RGBA_TMA
 #define H263_RGBA_TMA 1
-#endif
-// 1 = L2 prefetch of the prediction rows right after phase 0
-#ifndef H263_PREFETCH_PRED
-#define H263_PREFETCH_PRED 0
 #endif
 // BT.601 arithmetic: 0 = multiply-add + shift + saturating packs (v14), 1 = complemented terms, one clamp per channel,
 // 2 = 1 with the sample extraction as a dot product, 3 = 0 with extraction and shifts as dot products, 4 = 2 with green
@@ -57,16 +59,15 @@ constexpr int WARP_MBS = 4;  // macroblocks per warp
 #ifndef H263_RGBA_MODE
 #define H263_RGBA_MODE 4
 #endif
-constexpr int CTA_WARPS = H263_CTA_WARPS;
-constexpr int CTA_THREADS = CTA_WARPS * 32;
 constexpr int WARP_BLOCKS = WARP_MBS * 6;
 constexpr int RES_WORDS = 36;    // per slot: 8 residual rows of 8 x s16 (16 bytes) + 4 words of padding, which put
                                  // the four slots of a pass on different banks
-constexpr int EV_CAP = 96;       // events walked at once (one slot has at most 64); more are walked in chunks
+constexpr int EV_CAP = 64;       // events walked at once (one slot has at most 64); more are walked in chunks (1.4 % of
+                                 // the benchmark's tiles hold more than 64 events)
 constexpr int SLOT_FLOATS = 68;  // 64 + 4 pad: 16 B aligned, the four slots of a pass start 4 banks apart
 constexpr int STAGE_BYTES = 4096;  // RGBA of the warp's four macroblocks: 4 x (16 rows x 64 bytes)
 
-// per-macroblock flags (WarpTail.mb[][3])
+// per-macroblock flags (WarpTail.mba[].w)
 constexpr uint32_t MBF_INTER = 1u << 0;
 constexpr uint32_t MBF_LEFT = 1u << 2, MBF_RIGHT = 1u << 3, MBF_TOP = 1u << 4, MBF_BOTTOM = 1u << 5;
 constexpr uint32_t MBF_RGBA = 1u << 6;
@@ -78,32 +79,51 @@ struct __align__(16) WarpStage {
     uint32_t res[WARP_BLOCKS][RES_WORDS];  // per slot: residual rows, s16 row-major (row j = words 4j..4j+3)
     uint32_t evbuf[EV_CAP];                // walked events of the slots in flight: lin[5:0] | dropped[15] | value[31:16]
     uint2 slotdesc[WARP_BLOCKS];           // x = first event unit (absolute), y = nev | quant<<8 | wide<<13 | inter<<14 | chroma<<15 | block<<16 | dc<<24
-    uint32_t pad[16];
+    uint32_t sstart[WARP_BLOCKS];          // per slot: index of its first event among the warp's events
+    uint32_t slotinfo[WARP_BLOCKS];        // per slot, gathered by the walk: rows[7:0] | column > 0 [8] | overflow [9]; the
+                                           // classification (lane = slot) replaces it in place by
+                                           // rows to transform[7:0] | cls[10:8] | has_dc[11]
 };
 static_assert(sizeof(WarpStage) == STAGE_BYTES, "the RGBA tile aliases exactly this");
 
-struct __align__(16) WarpTail {
-    float coef[4][SLOT_FLOATS];        // coefficients of the four slots in flight
-    uint32_t mb[WARP_MBS][8];          // ydst4, cdst4, rgba row, flags, pitches, mbx, pic, edge info
-    uint32_t mbrec[WARP_BLOCKS];       // the four macroblock records
-    uint32_t bd[WARP_BLOCKS];          // per block: 4-byte offset (from the y or c pool) of the aligned word that holds
-                                       // the first source sample of the block's row 0 (blocks 4 and 5 share one)
-    uint32_t bf[WARP_BLOCKS];          // per block: BF_* flags
-    uint32_t meta[WARP_BLOCKS];        // per block: cls[2:0] | slot[7:3] | dcres[31:16]
-    uint32_t sstart[WARP_BLOCKS];      // per slot: index of its first event among the warp's events
-    uint32_t slotinfo[WARP_BLOCKS];    // per slot, gathered by the walk: rows[7:0] | column > 0 [8] | overflow [9]
-    uint32_t slotcls[WARP_BLOCKS];     // per slot after classification: rows to transform[7:0] | cls[10:8] | has_dc[11]
-    uint8_t order[WARP_BLOCKS];        // slots of the chunk sorted by rows to transform (most first)
-    uint8_t pad[8];
+// What lives from phase 0 to the end, plus the coefficient slots.  COMPACT (standard formats): the macroblock records are
+// dead after phase 0 and sit in the coefficient slots; pitches, picture index and edge info are not kept at all.
+template <bool COMPACT>
+struct WarpTailT;
+template <>
+struct __align__(16) WarpTailT<true> {
+    float coef[4][SLOT_FLOATS];     // coefficients of the four slots in flight
+    uint4 mba[WARP_MBS];            // ydst4, cdst4, rgba row, flags
+    uint32_t mbx[WARP_MBS];
+    uint32_t bd[WARP_BLOCKS];       // per block: 4-byte offset (from the y or c pool) of the aligned word that holds
+                                    // the first source sample of the block's row 0 (blocks 4 and 5 share one)
+    uint32_t meta[WARP_BLOCKS];     // per block: cls[2:0] | slot[7:3] | dcres[31:16]
+    uint8_t bf[WARP_BLOCKS];        // per block: BF_* flags
+    uint8_t order[WARP_BLOCKS];     // slots of the chunk sorted by rows to transform (most first)
+    __device__ __forceinline__ uint32_t* mbrec() { return reinterpret_cast<uint32_t*>(&coef[0][0]); }
+};
+template <>
+struct __align__(16) WarpTailT<false> {
+    float coef[4][SLOT_FLOATS];
+    uint4 mba[WARP_MBS];
+    uint32_t mbx[WARP_MBS];
+    uint4 mbb[WARP_MBS];            // pitches (y | c << 16), -, picture index, edge info
+    uint32_t bd[WARP_BLOCKS];
+    uint32_t meta[WARP_BLOCKS];
+    uint32_t mbrec_[WARP_BLOCKS];   // the four macroblock records (the clamped prediction path reads them again)
+    uint8_t bf[WARP_BLOCKS];
+    uint8_t order[WARP_BLOCKS];
+    __device__ __forceinline__ uint32_t* mbrec() { return mbrec_; }
 };
 
-// 8 CTAs x (23.5 + 1) KB fill the 196 KB shared-memory carve-out exactly; one more byte per CTA would take the
-// 228 KB carve-out and leave no L1 (8 % slower, profiles/r01_variants.txt)
-struct TileSmem {
-    WarpStage stage[CTA_WARPS];  // first: TMA store sources must be 128-byte aligned
-    WarpTail tail[CTA_WARPS];
+template <bool COMPACT, int NW>
+struct TileSmemT {
+    WarpStage stage[NW];  // first: TMA store sources must be 128-byte aligned
+    WarpTailT<COMPACT> tail[NW];
 };
-static_assert(sizeof(TileSmem) <= 24064 * CTA_WARPS / 4, "shared memory budget of 8 CTAs per SM");
+// the 196 KB carve-out holds 200 704 bytes, of which every resident CTA takes 1 KB besides its own shared memory
+static_assert(sizeof(TileSmemT<true, H263_STD_WARPS>) <= 200704 / H263_STD_CTAS - 1024, "shared memory budget of the standard instantiations");
+static_assert(sizeof(TileSmemT<false, GEN_WARPS>) <= 200704 / GEN_CTAS - 1024, "shared memory budget of the generic instantiations");
 
 __device__ const float g_basis[8][8] = H263_BASIS_TABLE;
 __device__ const uint8_t g_dezigzag[64] = H263_DEZIGZAG_LINEAR;
@@ -284,15 +304,18 @@ __device__ __forceinline__ uint32_t stage_offset(int q, int row, int c) { return
 // WIDE_MV: some vector of the step may leave the replicated border (no H263CU_PICFLAG_MV_IN_RANGE; unreachable from a
 // parsed stream, mvd_pred.rs:70-117): the instantiation with the clamped per-sample path.  Without it vectors are
 // clamped to the range in phase 0, and that path does not weigh on the register allocation.
-template <int PY, int PC, int PR, bool EDGE, bool WIDE_MV>
-__global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
+template <int PY, int PC, int PR, bool EDGE, bool WIDE_MV, int NW, int NCTAS>
+__global__ void __launch_bounds__(NW * 32, NCTAS)
     recon_tile_kernel(const PicDev* __restrict__ pics, const h263cu_mb* __restrict__ mbs,
                       const h263cu_event* __restrict__ events, uint32_t n_mbs, int emit_rgba, const Pools pools,
                       const __grid_constant__ CUtensorMap rgba_map) {
-    __shared__ __align__(1024) TileSmem S;
+    constexpr bool COMPACT = PY != 0 && !EDGE && !WIDE_MV;
+    constexpr int CTA_WARPS = NW;
+    __shared__ __align__(1024) TileSmemT<COMPACT, NW> S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpStage& G = S.stage[warp];
-    WarpTail& W = S.tail[warp];
+    WarpTailT<COMPACT>& W = S.tail[warp];
+    uint32_t* const mbrec = W.mbrec();
     const int g = lane >> 3, t = lane & 7;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -303,13 +326,13 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
     const int n_w = (int)min((uint32_t)WARP_MBS, n_mbs - mb0);
 
     // ================= phase 0: lane = block (macroblock lane / 6, block lane % 6) ==============
-    if (lane < n_w * 6) W.mbrec[lane] = __ldg(reinterpret_cast<const uint32_t*>(mbs) + (size_t)tile * WARP_BLOCKS + lane);
+    if (lane < n_w * 6) mbrec[lane] = __ldg(reinterpret_cast<const uint32_t*>(mbs) + (size_t)tile * WARP_BLOCKS + lane);
     __syncwarp();
     int n_slots;
     {
         const bool bvalid = lane < n_w * 6;
         const int bm = bvalid ? (lane * 43) >> 8 : 0, bb = bvalid ? lane - bm * 6 : 0;
-        const uint32_t* r = &W.mbrec[bm * 6];
+        const uint32_t* r = &mbrec[bm * 6];
         const uint32_t w0 = r[0], w1 = r[1], w2 = r[2], w3 = r[3], w4 = r[4], w5 = r[5];
         const uint32_t pic = w1 & 0xFFFFu;
         const PicDev& P = pics[pic];
@@ -353,7 +376,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         }
         if (bvalid) {
             W.bd[lane] = boff;
-            W.bf[lane] = bflags;
+            W.bf[lane] = (uint8_t)bflags;
             if (bb == 0) {
                 const int pitch_y = PY ? PY : P.pitch_y, pitch_c = PC ? PC : P.pitch_c;
                 const int mbw = (P.w + 15) >> 4, mbh = (P.h + 15) >> 4;
@@ -368,10 +391,10 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 if (mby == 0) flags |= MBF_TOP;
                 if (mby == mbh - 1) flags |= MBF_BOTTOM;
                 if (emit_rgba && P.rgba) flags |= MBF_RGBA;
-                *reinterpret_cast<uint4*>(&W.mb[bm][0]) =
-                    make_uint4(P.cur_y4 + (uint32_t)((mby * 16 * pitch_y + mbx * 16) >> 2),
-                               P.cur_c4 + (uint32_t)((mby * 8 * pitch_c + mbx * 16) >> 2), P.rgba_row0 + (uint32_t)(mby * 16), flags);
-                *reinterpret_cast<uint4*>(&W.mb[bm][4]) = make_uint4((uint32_t)pitch_y | ((uint32_t)pitch_c << 16), (uint32_t)mbx, pic, ed);
+                W.mba[bm] = make_uint4(P.cur_y4 + (uint32_t)((mby * 16 * pitch_y + mbx * 16) >> 2),
+                                       P.cur_c4 + (uint32_t)((mby * 8 * pitch_c + mbx * 16) >> 2), P.rgba_row0 + (uint32_t)(mby * 16), flags);
+                W.mbx[bm] = (uint32_t)mbx;
+                if constexpr (!COMPACT) W.mbb[bm] = make_uint4((uint32_t)pitch_y | ((uint32_t)pitch_c << 16), 0u, pic, ed);
             }
         }
 
@@ -386,7 +409,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         // events of the blocks before this one inside the macroblock
         const uint32_t before = (ev_incl - nev) - __shfl_sync(FULL, ev_incl - nev, bm * 6);
         if (coded) {
-            W.sstart[pos] = ev_incl - nev;
+            G.sstart[pos] = ev_incl - nev;
             const uint32_t first = P.first_event + w0 + (wide ? 2 * before : before);
             const uint32_t quant = (w2 >> 8) & 31u;
             G.slotdesc[pos] = make_uint2(first, nev | (quant << 8) | (wide ? 1u << 13 : 0u) | (inter ? 1u << 14 : 0u) |
@@ -401,24 +424,6 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
     }
     __syncwarp();
 
-#if H263_PREFETCH_PRED
-    // The prediction rows are read in phase 3, one event walk and one transform from here: ask the L2 for them now
-    // (lane = 4 luma columns x 8 rows as in phase 3; the request of a lane covers the sector its words lie in).
-    {
-        const int mbq = lane >> 3, rgrp = (lane >> 2) & 1, cg = lane & 3;
-        const int mbi = mbq < n_w ? mbq : 0;
-        if (W.mb[mbi][3] & MBF_INTER) {
-            const uint32_t pitch_y4 = PY ? PY / 4 : (W.mb[mbi][4] & 0xFFFFu) >> 2, pitch_c4 = PC ? PC / 4 : W.mb[mbi][4] >> 18;
-            const int lb = rgrp * 2 + (cg >> 1);
-            const uint32_t* sy = reinterpret_cast<const uint32_t*>(pools.y) + W.bd[mbi * 6 + lb] + (uint32_t)(cg & 1);
-            const uint32_t* sc = reinterpret_cast<const uint32_t*>(pools.c) + W.bd[mbi * 6 + 4] + (uint32_t)cg + (uint32_t)(rgrp * 4) * pitch_c4;
-#pragma unroll
-            for (int r = 0; r < 9; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(sy + (uint32_t)r * pitch_y4));
-#pragma unroll
-            for (int r = 0; r < 5; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc + (uint32_t)r * pitch_c4));
-        }
-    }
-#endif
 
     // ================= phases 1 + 2, per chunk of slots whose events fit the event buffer ==========
     // (one chunk unless the four macroblocks hold more than EV_CAP events)
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         if (H263_ABLATE & 1) n_slots = 0;
         const bool is_slot = lane < n_slots;
         const uint2 my_sd = is_slot ? G.slotdesc[lane] : make_uint2(0u, 0u);
-        const uint32_t my_start = is_slot ? W.sstart[lane] : 0xFFFFFFFFu;
+        const uint32_t my_start = is_slot ? G.sstart[lane] : 0xFFFFFFFFu;
         const uint32_t my_end = my_start + (my_sd.y & 0xFFu);
         int s_lo = 0;
         uint32_t e_lo = 0;
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             const bool in_chunk = lane >= s_lo && lane < s_hi;
             const uint32_t e_end = __shfl_sync(FULL, my_end, s_hi - 1);
             const uint32_t e_hi = min(e_end, e_lo + (uint32_t)EV_CAP);
-            if (in_chunk) W.slotinfo[lane] = 0u;
+            if (in_chunk) G.slotinfo[lane] = 0u;
             __syncwarp();
 
             // ---- phase 1: lane = event.  The zig-zag index is a segmented prefix sum of run + 1 over the
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 bool inter = false;
                 if (act) {
                     const uint2 sd = G.slotdesc[slot];
-                    const uint32_t k = e - W.sstart[slot];
+                    const uint32_t k = e - G.sstart[slot];
                     const int quant = (int)((sd.y >> 8) & 31u);
                     inter = (sd.y >> 14) & 1u;
                     int run;
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                         bits = 0x200u;
                     }
                     G.evbuf[e - e_lo] = ent;
-                    atomicOr(&W.slotinfo[slot], bits);
+                    atomicOr(&G.slotinfo[slot], bits);
                 }
             }
             __syncwarp();
@@ -503,7 +508,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             // ---- classification, lane = slot (rle.rs:94-171) ----
             int key = 4;
             if (in_chunk) {
-                const uint32_t info = W.slotinfo[lane];
+                const uint32_t info = G.slotinfo[lane];
                 const bool inter = (my_sd.y >> 14) & 1u;
                 const uint32_t blk = (my_sd.y >> 16) & 0xFFu, code = my_sd.y >> 24;
                 const bool ovf = (info & 0x200u) != 0, col = (info & 0x100u) != 0;
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                     R = rows | (has_dc ? 1u : 0u);
                 }
                 W.meta[blk] = (uint32_t)cls | ((uint32_t)lane << 3) | ((uint32_t)dcres << 16);
-                W.slotcls[lane] = R | ((uint32_t)cls << 8) | (has_dc ? 0x800u : 0u);
+                G.slotinfo[lane] = R | ((uint32_t)cls << 8) | (has_dc ? 0x800u : 0u);
                 const int n = __popc(R);
                 key = n >= 4 ? 0 : (n >= 2 ? 1 : (n == 1 ? 2 : 3));
             }
@@ -545,12 +550,12 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 const int si = si0 + g;
                 const bool valid = si < s_lo + n_need;
                 const int sl = valid ? (int)W.order[si] : 0;
-                const uint32_t sc = valid ? W.slotcls[sl] : 0u;
+                const uint32_t sc = valid ? G.slotinfo[sl] : 0u;
                 const uint32_t R = sc & 0xFFu;
                 const bool vert = ((sc >> 8) & 7u) == CLS_VERT;
                 const uint2 sd = G.slotdesc[sl];
                 const int nev = valid ? (int)(sd.y & 0xFFu) : 0;
-                const uint32_t first = W.sstart[sl] - e_lo;
+                const uint32_t first = G.sstart[sl] - e_lo;
                 // lane t clears row t of the slot, then the slot's events are scattered into it
                 *reinterpret_cast<float4*>(c + t * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4*>(c + t * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -631,8 +636,12 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         const int mbq = lane >> 3, rgrp = (lane >> 2) & 1, cg = lane & 3;
         const bool unit_ok = mbq < n_w;
         const int mbi = unit_ok ? mbq : 0;
-        const uint4 ma = *reinterpret_cast<const uint4*>(&W.mb[mbi][0]);
-        const uint4 mv = *reinterpret_cast<const uint4*>(&W.mb[mbi][4]);
+        const uint4 ma = W.mba[mbi];
+        uint4 mv = make_uint4(0u, W.mbx[mbi], 0u, 0u);  // pitches, mbx, picture index, edge info
+        if constexpr (!COMPACT) {
+            const uint4 b = W.mbb[mbi];
+            mv.x = b.x, mv.z = b.z, mv.w = b.w;
+        }
         const uint32_t flags = (unit_ok ? ma.w : 0u) & ~((H263_ABLATE & 2) ? MBF_INTER : 0u) & ~((H263_ABLATE & 4) ? MBF_RGBA : 0u);
         const uint32_t pitch_y4 = PY ? PY / 4 : (mv.x & 0xFFFFu) >> 2, pitch_c4 = PC ? PC / 4 : mv.x >> 18;
         const int lb = rgrp * 2 + (cg >> 1);  // luma block of this lane
@@ -669,7 +678,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
             } else {
                 // vector beyond the replicated border: clamped per-sample fetch (read_sample, gather.rs:16-31)
                 const PicDev& P = pics[mv.z];
-                const uint32_t* rr = &W.mbrec[mbi * 6];
+                const uint32_t* rr = &mbrec[mbi * 6];
                 const uint32_t w1 = rr[1];
                 const uint32_t mvw = lb < 2 ? (rr[4] >> (16 * lb)) : (rr[5] >> (16 * (lb - 2)));
                 const int mvx = (int8_t)(mvw & 0xFF), mvy = (int8_t)((mvw >> 8) & 0xFF);
@@ -705,7 +714,7 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
                 }
             } else {
                 const PicDev& P = pics[mv.z];
-                const uint32_t* rr = &W.mbrec[mbi * 6];
+                const uint32_t* rr = &mbrec[mbi * 6];
                 const uint32_t w1 = rr[1], w4 = rr[4], w5 = rr[5];
                 const int sumx = (int8_t)byte_of(w4, 0) + (int8_t)byte_of(w4, 2) + (int8_t)byte_of(w5, 0) + (int8_t)byte_of(w5, 2);
                 const int sumy = (int8_t)byte_of(w4, 1) + (int8_t)byte_of(w4, 3) + (int8_t)byte_of(w5, 1) + (int8_t)byte_of(w5, 3);
@@ -876,11 +885,11 @@ __global__ void __launch_bounds__(CTA_THREADS, H263_MIN_CTAS)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane < n_w) {
-            const uint32_t f = W.mb[lane][3] & ~((H263_ABLATE & (4 | 16)) ? MBF_RGBA : 0u);
+            const uint32_t f = W.mba[lane].w & ~((H263_ABLATE & (4 | 16)) ? MBF_RGBA : 0u);
             if (f & MBF_RGBA) {
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(&G) + (uint32_t)lane * 1024u;
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&rgba_map), "r"(src),
-                             "r"((int)(W.mb[lane][5] * 64u)), "r"((int)W.mb[lane][2])
+                             "r"((int)(W.mbx[lane] * 64u)), "r"((int)W.mba[lane].z)
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -953,28 +962,27 @@ int recon_tile_uses_tma() { return H263_RGBA_TMA; }
 void launch_recon_tile(const PicDev* pics, const h263cu_mb* mbs, const h263cu_event* events, uint32_t n_mbs, int emit_rgba,
                        int unaligned, int wide_mv, const Pools& pools, const CUtensorMap* rgba_map, cudaStream_t stream) {
     if (n_mbs == 0) return;
-    const uint32_t per_cta = CTA_WARPS * WARP_MBS;
-    const uint32_t grid = (n_mbs + per_cta - 1) / per_cta;
     // pitches of the standard formats (context.cu: pitch_y = pitch_c = 16 * mbw + 64, rgba = 64 * mbw)
     const uint32_t py = pools.pitch_y, pc = pools.pitch_c, pr = pools.rgba_pitch;
     const CUtensorMap& tm = *rgba_map;
-#define H263_LAUNCH(PY_, PC_, PR_, EDGE_, WIDE_) \
-    recon_tile_kernel<PY_, PC_, PR_, EDGE_, WIDE_><<<grid, CTA_THREADS, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools, tm)
+#define H263_LAUNCH(PY_, PC_, PR_, EDGE_, WIDE_, NW_, NCTAS_)                                                                      \
+    recon_tile_kernel<PY_, PC_, PR_, EDGE_, WIDE_, NW_, NCTAS_>                                                                    \
+        <<<(n_mbs + NW_ * WARP_MBS - 1) / (NW_ * WARP_MBS), NW_ * 32, 0, stream>>>(pics, mbs, events, n_mbs, emit_rgba, pools, tm)
     if (wide_mv) {  // hand-built side info with vectors beyond the range: clamped per-sample path, run-time pitches
         if (unaligned)
-            H263_LAUNCH(0, 0, 0, true, true);
+            H263_LAUNCH(0, 0, 0, true, true, GEN_WARPS, GEN_CTAS);
         else
-            H263_LAUNCH(0, 0, 0, false, true);
+            H263_LAUNCH(0, 0, 0, false, true, GEN_WARPS, GEN_CTAS);
     } else if (unaligned)  // some picture of the step is not a multiple of 16 in size: edge fix-up, run-time pitches
-        H263_LAUNCH(0, 0, 0, true, false);
+        H263_LAUNCH(0, 0, 0, true, false, GEN_WARPS, GEN_CTAS);
     else if (py == 416 && pc == 416 && pr == 1408)  // CIF 352x288
-        H263_LAUNCH(416, 416, 1408, false, false);
+        H263_LAUNCH(416, 416, 1408, false, false, H263_STD_WARPS, H263_STD_CTAS);
     else if (py == 240 && pc == 240 && pr == 704)  // QCIF 176x144
-        H263_LAUNCH(240, 240, 704, false, false);
+        H263_LAUNCH(240, 240, 704, false, false, H263_STD_WARPS, H263_STD_CTAS);
     else if (py == 768 && pc == 768 && pr == 2816)  // 4CIF 704x576
-        H263_LAUNCH(768, 768, 2816, false, false);
+        H263_LAUNCH(768, 768, 2816, false, false, H263_STD_WARPS, H263_STD_CTAS);
     else
-        H263_LAUNCH(0, 0, 0, false, false);
+        H263_LAUNCH(0, 0, 0, false, false, GEN_WARPS, GEN_CTAS);
 #undef H263_LAUNCH
 }
 
