@@ -155,3 +155,45 @@ def test_deblock_process_both_semantics(dm):
                 assert list(arr) == exp, (q, s, trunc)
             else:
                 assert list(arr) == [int(v) for v in q]  # strength 0: no-op
+
+
+def test_identities_of_the_v15_recon_kernel_hold_for_every_input():
+    """The recon kernel's epilogue replaces three pieces of the reference's arithmetic by identities (recon_tile.cu);
+    each is checked here over its whole input domain, in integers, with the semantics of the SASS instructions used:
+      * BT.601 (bt601.rs:12-59) on complemented terms: clamp(0xFFFFFF - x, 0, 0xFFFFFF) carries 255 - clamp(x >> 16, 0, 255)
+        in byte 2 and 0 in byte 3 -- all 2^24 (y, cb, cr);
+      * average_sum_of_mvs (types.rs:759-768) = ((s + 13) >> 4) + ((s + 2) >> 4) -- every sum of four i8 vectors;
+      * the even lanes of a + b as (a + b) - 256 (O_a + O_b) modulo 2^32 -- random words."""
+    y = np.arange(256, dtype=np.int64)[:, None, None]
+    cb = np.arange(256, dtype=np.int64)[None, :, None]
+    cr = np.arange(256, dtype=np.int64)[None, None, :]
+    gray = (y - 16) * 76309
+    ref = {
+        "r": np.clip((gray + (cr - 128) * 104597 + 32768) >> 16, 0, 255) + 0 * cb,
+        "g": np.clip((gray + (cr - 128) * -53279 + (cb - 128) * -25675 + 32768) >> 16, 0, 255),
+        "b": np.clip((gray + (cb - 128) * 132201 + 32768) >> 16, 0, 255) + 0 * cr,
+    }
+    # the kernel's terms: t'_c = 0xFFFFFF - t_c with t_c = chroma part + 32768 - 16 * 76309 (folded constants)
+    tr = cr * -104597 + (0xFFFFFF - (32768 - 128 * 104597 - 16 * 76309))
+    tg = cr * 53279 + cb * 25675 + (0xFFFFFF - (32768 + 128 * 53279 + 128 * 25675 - 16 * 76309))
+    tb = cb * -132201 + (0xFFFFFF - (32768 - 128 * 132201 - 16 * 76309))
+    xr = y * -76309 + tr  # one IMAD
+    dg, db = tg - tr, tb - tr  # green / blue as differences from red (added inside VIADDMNMX.RELU)
+    for name, w in (("r", xr + 0 * cb), ("g", xr + dg), ("b", xr + db)):
+        assert np.abs(w).max() < 2 ** 31  # no 32-bit overflow anywhere
+        wc = np.clip(w, 0, 0xFFFFFF)  # max(min(a + b, c), 0)
+        assert np.array_equal(255 - ((wc >> 16) & 0xFF), ref[name]), name
+        assert not (wc >> 24).any()
+
+    s = np.arange(-4 * 128, 4 * 127 + 1)
+    whole, frac = (s >> 4) << 1, s & 15
+    ref_avg = np.where(frac <= 2, whole, np.where(frac >= 14, whole + 2, whole + 1))
+    assert np.array_equal(((s + 13) >> 4) + ((s + 2) >> 4), ref_avg)
+
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 2 ** 32, 200000, dtype=np.uint64)
+    b = rng.integers(0, 2 ** 32, 200000, dtype=np.uint64)
+    M = np.uint64(0x00FF00FF)
+    odd = ((a >> np.uint64(8)) & M) + ((b >> np.uint64(8)) & M)
+    even = ((a + b) - np.uint64(256) * odd) & np.uint64(0xFFFFFFFF)
+    assert np.array_equal(even, (a & M) + (b & M))
