@@ -24,6 +24,12 @@
 // macroblock rows (v13: 16-20 luma, 32 chroma) -- the L1 look-ups that bounded v13.
 // Everything a lane needs per block sits in shared memory as 32-bit offsets from the context's
 // pool bases (kernel parameters), so the epilogue does no 64-bit pointer chasing.
+//
+// v15 / v16 (profiles/r02_variants.txt): the kernel is bound by the ALU pipe and the issue slots, so
+// integer work sits on the multiply pipe where it costs the same number of instructions (byte extraction and vector
+// sums as IDP.4A dot products, plane words and even lanes as multiply-adds), BT.601 runs on complemented terms (one
+// clamp instruction per channel), the RGBA tile is handed to the TMA unit before the plane stores, and the standard
+// instantiations keep 5.4 KB of shared memory per warp so that 35 warps fit an SM beside the L1.
 #include "recon_common.cuh"
 
 namespace h263dev {
@@ -302,8 +308,10 @@ __device__ __forceinline__ uint32_t stage_offset(int q, int row, int c) { return
 // stores (and the border replication continues from there), so that prediction reads beyond the true edge see
 // read_sample's clamp (gather.rs:16-31).  Compiled out of the instantiations for aligned pictures.
 // WIDE_MV: some vector of the step may leave the replicated border (no H263CU_PICFLAG_MV_IN_RANGE; unreachable from a
-// parsed stream, mvd_pred.rs:70-117): the instantiation with the clamped per-sample path.  Without it vectors are
-// clamped to the range in phase 0, and that path does not weigh on the register allocation.
+// parsed stream, mvd_pred.rs:70-117): the instantiation with the clamped per-sample path.  Without it every vector of
+// the step lies in the range (the parser cannot leave it, caller-built side info is checked on the host), nothing is
+// clamped, and that path does not weigh on the register allocation.
+// NW / NCTAS: warps per CTA and CTAs per SM (5 x 7 for the standard formats, 4 x 8 otherwise).
 template <int PY, int PC, int PR, bool EDGE, bool WIDE_MV, int NW, int NCTAS>
 __global__ void __launch_bounds__(NW * 32, NCTAS)
     recon_tile_kernel(const PicDev* __restrict__ pics, const h263cu_mb* __restrict__ mbs,
