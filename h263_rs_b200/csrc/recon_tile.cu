@@ -73,7 +73,7 @@ constexpr int EV_CAP = 64;       // events walked at once (one slot has at most 
 constexpr int SLOT_FLOATS = 68;  // 64 + 4 pad: 16 B aligned, the four slots of a pass start 4 banks apart
 constexpr int STAGE_BYTES = 4096;  // RGBA of the warp's four macroblocks: 4 x (16 rows x 64 bytes)
 
-// per-macroblock flags (WarpTail.mba[].w)
+// per-macroblock flags (WarpTail.mba[].w, low byte; mbx sits above them)
 constexpr uint32_t MBF_INTER = 1u << 0;
 constexpr uint32_t MBF_LEFT = 1u << 2, MBF_RIGHT = 1u << 3, MBF_TOP = 1u << 4, MBF_BOTTOM = 1u << 5;
 constexpr uint32_t MBF_RGBA = 1u << 6;
@@ -86,9 +86,9 @@ struct __align__(16) WarpStage {
     uint32_t evbuf[EV_CAP];                // walked events of the slots in flight: lin[5:0] | dropped[15] | value[31:16]
     uint2 slotdesc[WARP_BLOCKS];           // x = first event unit (absolute), y = nev | quant<<8 | wide<<13 | inter<<14 | chroma<<15 | block<<16 | dc<<24
     uint32_t sstart[WARP_BLOCKS];          // per slot: index of its first event among the warp's events
-    uint32_t slotinfo[WARP_BLOCKS];        // per slot, gathered by the walk: rows[7:0] | column > 0 [8] | overflow [9]; the
-                                           // classification (lane = slot) replaces it in place by
-                                           // rows to transform[7:0] | cls[10:8] | has_dc[11]
+    uint32_t slotinfo[WARP_BLOCKS];        // per slot, gathered by the walk: rows[7:0] | column > 0 [8] | overflow [9]; after
+                                           // the classification: the pass descriptors of the slots that need the
+                                           // transform, sorted by rows to transform (most first)
 };
 static_assert(sizeof(WarpStage) == STAGE_BYTES, "the RGBA tile aliases exactly this");
 
@@ -99,26 +99,22 @@ struct WarpTailT;
 template <>
 struct __align__(16) WarpTailT<true> {
     float coef[4][SLOT_FLOATS];     // coefficients of the four slots in flight
-    uint4 mba[WARP_MBS];            // ydst4, cdst4, rgba row, flags
-    uint32_t mbx[WARP_MBS];
+    uint4 mba[WARP_MBS];            // ydst4, cdst4, rgba row, flags[7:0] | mbx[15:8]
     uint32_t bd[WARP_BLOCKS];       // per block: 4-byte offset (from the y or c pool) of the aligned word that holds
                                     // the first source sample of the block's row 0 (blocks 4 and 5 share one)
     uint32_t meta[WARP_BLOCKS];     // per block: cls[2:0] | slot[7:3] | dcres[31:16]
     uint8_t bf[WARP_BLOCKS];        // per block: BF_* flags
-    uint8_t order[WARP_BLOCKS];     // slots of the chunk sorted by rows to transform (most first)
     __device__ __forceinline__ uint32_t* mbrec() { return reinterpret_cast<uint32_t*>(&coef[0][0]); }
 };
 template <>
 struct __align__(16) WarpTailT<false> {
     float coef[4][SLOT_FLOATS];
     uint4 mba[WARP_MBS];
-    uint32_t mbx[WARP_MBS];
     uint4 mbb[WARP_MBS];            // pitches (y | c << 16), -, picture index, edge info
     uint32_t bd[WARP_BLOCKS];
     uint32_t meta[WARP_BLOCKS];
     uint32_t mbrec_[WARP_BLOCKS];   // the four macroblock records (the clamped prediction path reads them again)
     uint8_t bf[WARP_BLOCKS];
-    uint8_t order[WARP_BLOCKS];
     __device__ __forceinline__ uint32_t* mbrec() { return mbrec_; }
 };
 
@@ -400,8 +396,8 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
                 if (mby == mbh - 1) flags |= MBF_BOTTOM;
                 if (emit_rgba && P.rgba) flags |= MBF_RGBA;
                 W.mba[bm] = make_uint4(P.cur_y4 + (uint32_t)((mby * 16 * pitch_y + mbx * 16) >> 2),
-                                       P.cur_c4 + (uint32_t)((mby * 8 * pitch_c + mbx * 16) >> 2), P.rgba_row0 + (uint32_t)(mby * 16), flags);
-                W.mbx[bm] = (uint32_t)mbx;
+                                       P.cur_c4 + (uint32_t)((mby * 8 * pitch_c + mbx * 16) >> 2), P.rgba_row0 + (uint32_t)(mby * 16),
+                                       flags | ((uint32_t)mbx << 8));
                 if constexpr (!COMPACT) W.mbb[bm] = make_uint4((uint32_t)pitch_y | ((uint32_t)pitch_c << 16), 0u, pic, ed);
             }
         }
@@ -515,6 +511,7 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
 
             // ---- classification, lane = slot (rle.rs:94-171) ----
             int key = 4;
+            uint32_t pd = 0u;
             if (in_chunk) {
                 const uint32_t info = G.slotinfo[lane];
                 const bool inter = (my_sd.y >> 14) & 1u;
@@ -536,7 +533,10 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
                     R = rows | (has_dc ? 1u : 0u);
                 }
                 W.meta[blk] = (uint32_t)cls | ((uint32_t)lane << 3) | ((uint32_t)dcres << 16);
-                G.slotinfo[lane] = R | ((uint32_t)cls << 8) | (has_dc ? 0x800u : 0u);
+                // everything a pass needs to know about the slot, in one word: slot[4:0] | rows to transform[12:5] |
+                // Vert[13] | intra DC present[14] | first event inside the chunk[21:15] | events[29:22] | chroma[30]
+                pd = (uint32_t)lane | (R << 5) | (cls == CLS_VERT ? 1u << 13 : 0u) | (has_dc ? 1u << 14 : 0u) | ((my_start - e_lo) << 15) |
+                     ((my_sd.y & 0xFFu) << 22) | ((my_sd.y & 0x8000u) << 15);
                 const int n = __popc(R);
                 key = n >= 4 ? 0 : (n >= 2 ? 1 : (n == 1 ? 2 : 3));
             }
@@ -550,20 +550,20 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
                 if (j == key) pos += __popc(b & lt_mask);
                 n_need += __popc(b);
             }
-            if (key < 3) W.order[pos] = (uint8_t)lane;
+            __syncwarp();  // every lane has read the walk's word of its slot: the sorted descriptors replace them
+            if (key < 3) G.slotinfo[pos] = pd;
             __syncwarp();
 
             // ---- phase 2: 4 slots per pass, 8 lanes per slot, lane t = column i of the block ---------
             for (int si0 = s_lo; si0 < s_lo + n_need; si0 += 4) {
                 const int si = si0 + g;
                 const bool valid = si < s_lo + n_need;
-                const int sl = valid ? (int)W.order[si] : 0;
-                const uint32_t sc = valid ? G.slotinfo[sl] : 0u;
-                const uint32_t R = sc & 0xFFu;
-                const bool vert = ((sc >> 8) & 7u) == CLS_VERT;
-                const uint2 sd = G.slotdesc[sl];
-                const int nev = valid ? (int)(sd.y & 0xFFu) : 0;
-                const uint32_t first = G.sstart[sl] - e_lo;
+                const uint32_t pd = valid ? G.slotinfo[si] : 0u;
+                const int sl = (int)(pd & 31u);
+                const uint32_t R = (pd >> 5) & 0xFFu;
+                const bool vert = (pd >> 13) & 1u;
+                const int nev = (int)((pd >> 22) & 0xFFu);
+                const uint32_t first = (pd >> 15) & 127u;
                 // lane t clears row t of the slot, then the slot's events are scattered into it
                 *reinterpret_cast<float4*>(c + t * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4*>(c + t * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -579,8 +579,8 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
                         c[ent & 63u] = (float)((int)ent >> 16);
                     }
                 }
-                if (sc & 0x800u) {
-                    if (t == 0) c[0] = (float)intradc_level((int)(sd.y >> 24));
+                if (pd & 0x4000u) {
+                    if (t == 0) c[0] = (float)intradc_level((int)(G.slotdesc[sl].y >> 24));
                 }
                 // Per row y that holds a coefficient in ANY of the four slots (warp-uniform skip otherwise):
                 //   row pass    t[y][i] = sum_x c[y][x] * B[x][i], ascending x (idct_1d, idct.rs:52-65), pre-divided
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
                     // so only the saturating add of phase 3 clamps.
                     // luma slots keep the columns of each group of four as (0, 2, 1, 3): the two words a lane of phase 3
                     // reads per row are then its even and its odd samples, the split its registers use
-                    uint16_t* rrow = reinterpret_cast<uint16_t*>(&G.res[sl][0]) + ((sd.y & 0x8000u) ? t : tperm);
+                    uint16_t* rrow = reinterpret_cast<uint16_t*>(&G.res[sl][0]) + ((pd & 0x40000000u) ? t : tperm);
                     if (any_vert) {  // rare: a block with coefficients in its first column only
                         const float m = vert ? H263_B00 : 1.0f;
 #pragma unroll
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
         const bool unit_ok = mbq < n_w;
         const int mbi = unit_ok ? mbq : 0;
         const uint4 ma = W.mba[mbi];
-        uint4 mv = make_uint4(0u, W.mbx[mbi], 0u, 0u);  // pitches, mbx, picture index, edge info
+        uint4 mv = make_uint4(0u, (ma.w >> 8) & 0xFFu, 0u, 0u);  // pitches, mbx, picture index, edge info
         if constexpr (!COMPACT) {
             const uint4 b = W.mbb[mbi];
             mv.x = b.x, mv.z = b.z, mv.w = b.w;
@@ -765,10 +765,12 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
                     yhi[r] = __viaddmin_s16x2_relu(yhi[r], rv.y, 0x00FF00FFu);
                 }
             }
+            // blocks 4 and 5 of a macroblock sit at an even index: one 64-bit load for both words
+            const uint2 mcc = *reinterpret_cast<const uint2*>(&W.meta[bc]);
 #pragma unroll
             for (int pl = 0; pl < 2; pl++) {
                 uint32_t(&cc)[4] = pl ? crp : cbp;
-                const uint32_t mc = W.meta[bc + pl];
+                const uint32_t mc = pl ? mcc.y : mcc.x;
                 const int ccls = (int)(mc & 7u);
                 if (ccls == CLS_DC) {
                     const uint32_t dd = __byte_perm(mc, 0, 0x3232);
@@ -897,7 +899,7 @@ __global__ void __launch_bounds__(NW * 32, NCTAS)
             if (f & MBF_RGBA) {
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(&G) + (uint32_t)lane * 1024u;
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&rgba_map), "r"(src),
-                             "r"((int)(W.mbx[lane] * 64u)), "r"((int)W.mba[lane].z)
+                             "r"((int)((f >> 8 & 0xFFu) * 64u)), "r"((int)W.mba[lane].z)
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
