@@ -175,12 +175,14 @@ __device__ __forceinline__ uint32_t vmix(uint32_t top, uint32_t bottom, uint32_t
     return __byte_perm(top * wt + (bottom * wb + 0x00800080u), 0, 0x4341);
 }
 
-// ---- BT.601 (bt601.rs:12-59), two instructions of clamp + pack per pixel ------------------
+// ---- BT.601 (bt601.rs:12-59) ----------------------------------------------------------------
+#if H263_RGBA_MODE == 0 || H263_RGBA_MODE == 3
 __device__ __forceinline__ uint32_t pack_sat(int a, int b, uint32_t c) {
     uint32_t d;  // d = c[15:0] << 16 | sat_u8(a) << 8 | sat_u8(b)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+#endif
 struct CT {
     int r, g, b;
 };
